@@ -1,0 +1,101 @@
+// Shared device/host helpers for the ideal-ballooning kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/ibs_b200.h"
+
+namespace ibs {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define IBS_CUDA_CHECK(expr)                                          \
+    do {                                                              \
+        cudaError_t _e = (expr);                                      \
+        if (_e != cudaSuccess) return ::ibs::cuda_fail(_e, #expr);    \
+    } while (0)
+
+#define IBS_REQUIRE(cond, msg)                                        \
+    do {                                                              \
+        if (!(cond)) {                                                \
+            ::ibs::set_error(std::string("invalid argument: ") + msg);\
+            return IBS_ERR_INVALID;                                   \
+        }                                                             \
+    } while (0)
+
+int num_sms();
+
+// Argument block of the solver kernels (K2+K3), shared by ibs_solver.cu and ibs_api.cu.
+struct SolveParams {
+    // coefficient source, mode "gcf"
+    const double* g; const double* c; const double* f;
+    // coefficient source, mode "base"
+    const double* base; const double* dPdrho; const double* theta0; const int* line_of_solve; int nth0;
+    int nsolve, N; double h;
+    const double* lam0; const double* sigma;
+    double* lam_out; double* lam_matrix_out; double* X_out; double* dX_out;
+    double* g_out; double* c_out; double* f_out; int* info_out;
+    // count-only mode
+    const double* lam_query; int* count_out;
+};
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- bit-level helpers on doubles -------------------------------------------------------------
+__device__ __forceinline__ int exp_of(double v) {          // floor(log2|v|) for normal v
+    return ((__double2hiint(v) >> 20) & 0x7ff) - 1023;
+}
+__device__ __forceinline__ double pow2i(int e) {            // 2^e, e clamped to the normal range
+    e = max(-1022, min(1023, e));
+    return __hiloint2double((e + 1023) << 20, 0);
+}
+__device__ __forceinline__ unsigned sign_word(double v) { return (unsigned)__double2hiint(v); }
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(FULL, v, d); }
+__device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_down_sync(FULL, v, d); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// Simpson weights of scipy.integrate.simpson with unit spacing (the reference's `simps(y)`,
+// utils.py:1621).  Odd N: composite 1/3 rule.  Even N: 1/3 rule on the first N-1 points plus the
+// Cartwright correction scipy >= 1.11 applies to the last interval (5/12, 2/3, -1/12).
+__host__ __device__ __forceinline__ double simpson_weight(int p, int N) {
+    const double third = 1.0 / 3.0;
+    if (N & 1) {
+        if (p == 0 || p == N - 1) return third;
+        return (p & 1) ? 4.0 * third : 2.0 * third;
+    }
+    if (N == 2) return 0.5;
+    double w = 0.0;
+    const int L = N - 1;   // points covered by the basic rule
+    if (p < L) w = (p == 0 || p == L - 1) ? third : ((p & 1) ? 4.0 * third : 2.0 * third);
+    if (p == N - 1) w += 5.0 / 12.0;
+    if (p == N - 2) w += 2.0 / 3.0;
+    if (p == N - 3) w -= 1.0 / 12.0;
+    return w;
+}
+
+}  // namespace ibs

@@ -1,0 +1,452 @@
+// K1: field-line geometry assembly.  Replaces the hot-path subset of vmec_fieldlines
+// (/root/reference/utils.py:161-864): theta_vmec root solve (:391-416), the 19 Fourier mode sums the
+// ballooning path needs (:420-468), the Cartesian dual basis and drifts (:474-658) and the GS2
+// normalisations (:662-720).  fp64 throughout; FP64-pipe bound (no tensor cores: the contraction has
+// only 10 / 9 output rows per mode set, a poor DMMA shape, and the trig generation is not a GEMM).
+//
+// Layout / mapping
+//   * One CTA works on one surface at a time; the surface's Fourier tables are re-packed on the fly
+//     (pack kernels below) into a dense (m, n) grid  tab[m][n_idx][ROW]  so that the inner n loop can be
+//     fully unrolled with compile-time signs and n-weights, and are staged into shared memory with one
+//     TMA bulk copy (cp.async.bulk + mbarrier) per table.  All threads then read the same coefficient
+//     at the same time: broadcast LDS.128, no bank conflicts.
+//   * One thread = one point of a field line.  cos/sin(n nfp phi) for n = 0..NT live in registers
+//     (angle-addition recurrence from one sincos), cos/sin(m theta) advance by recurrence in the m loop,
+//     so cos(m theta - n phi) costs 2 FMA-pairs instead of a sincos per mode: 30 sincos per point
+//     instead of 634 for NCSX.
+//   * The Newton solve for theta_vmec uses the n-sums A_m = sum_n l_mn cos(n phi), B_m = sum_n l_mn
+//     sin(n phi), which are fixed along the iteration, so each iteration costs O(mpol), not O(mnmax).
+#include <mutex>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "ibs_common.cuh"
+
+namespace ibs {
+
+constexpr int GEO_THREADS = 128;
+constexpr int ROW_MN = 10;    // r, n r, r_s, z, n z, z_s, l, n l, l_s, (pad)
+constexpr int ROW_NYQ = 8;    // g, b, n b, b_s, bsupv, bsubs, bsubu, bsubv
+constexpr int MAX_M_NEWTON = 96;
+
+struct GeoParams {
+    const double* pk_mn;    // [ns][M1][W1][ROW_MN]
+    const double* pk_nyq;   // [ns][M2][W2][ROW_NYQ]
+    const double* scal;     // [ns][8]
+    const double* alpha; int nalpha; int alpha_per_surface;
+    const double* theta; int nl;
+    int ns, M1, M2;         // number of m values in each set
+    int nfp;                // toroidal stride of the packed n index
+    double phi_center, psi_e, L_ref;
+    double* base_out; double* theta_vmec_out; int* info_out;
+};
+
+// ---- pack kernels: (ns, rows, mn) tables -> dense (m, n_idx) grid with the n-weights folded in -----------
+__global__ void pack_mn_kernel(const double* __restrict__ tab, const int* __restrict__ mode_m, const int* __restrict__ mode_n,
+                               int ns, int mnmax, int M1, int W1, int NT1, int nfp, double* __restrict__ out) {
+    const int s = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= mnmax) return;
+    const int m = mode_m[k], nn = mode_n[k];          // nn = n / nfp
+    const double* t = tab + (size_t)s * 6 * mnmax;
+    double* o = out + (((size_t)s * M1 + m) * W1 + (nn + NT1)) * ROW_MN;
+    const double n = (double)(nn * nfp);
+    const double r = t[0 * mnmax + k], z = t[1 * mnmax + k], l = t[2 * mnmax + k];
+    // duplicates in the mode list are legal (they add up)
+    atomicAdd(o + 0, r); atomicAdd(o + 1, n * r); atomicAdd(o + 2, t[3 * mnmax + k]);
+    atomicAdd(o + 3, z); atomicAdd(o + 4, n * z); atomicAdd(o + 5, t[4 * mnmax + k]);
+    atomicAdd(o + 6, l); atomicAdd(o + 7, n * l); atomicAdd(o + 8, t[5 * mnmax + k]);
+}
+__global__ void pack_nyq_kernel(const double* __restrict__ tab, const int* __restrict__ mode_m, const int* __restrict__ mode_n,
+                                int ns, int mnmax, int M2, int W2, int NT2, int nfp, double* __restrict__ out) {
+    const int s = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= mnmax) return;
+    const int m = mode_m[k], nn = mode_n[k];
+    const double* t = tab + (size_t)s * 7 * mnmax;
+    double* o = out + (((size_t)s * M2 + m) * W2 + (nn + NT2)) * ROW_NYQ;
+    const double n = (double)(nn * nfp);
+    const double b = t[1 * mnmax + k];
+    atomicAdd(o + 0, t[0 * mnmax + k]); atomicAdd(o + 1, b); atomicAdd(o + 2, n * b); atomicAdd(o + 3, t[2 * mnmax + k]);
+    atomicAdd(o + 4, t[3 * mnmax + k]); atomicAdd(o + 5, t[4 * mnmax + k]); atomicAdd(o + 6, t[5 * mnmax + k]);
+    atomicAdd(o + 7, t[6 * mnmax + k]);
+}
+
+// ---- TMA bulk copy global -> shared, completion on an mbarrier -------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+
+// cos/sin(m theta - n phi) for one n_idx with compile-time sign
+template <int SGN> __device__ __forceinline__ void angle(double cm, double sm, double cn, double sn, double& ca, double& sa) {
+    if (SGN >= 0) { ca = fma(cm, cn, sm * sn); sa = fma(sm, cn, -(cm * sn)); }      // n >= 0: m th - |n| ph
+    else          { ca = fma(cm, cn, -(sm * sn)); sa = fma(sm, cn, cm * sn); }      // n <  0: m th + |n| ph
+}
+
+template <int NT1, int NT2>
+__global__ void __launch_bounds__(GEO_THREADS)
+geometry_kernel(const GeoParams p) {
+    constexpr int W1 = 2 * NT1 + 1, W2 = 2 * NT2 + 1, NT = (NT1 > NT2 ? NT1 : NT2);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* s_mn = reinterpret_cast<double*>(smem_raw + 16);
+    const int n_mn = p.M1 * W1 * ROW_MN, n_nyq = p.M2 * W2 * ROW_NYQ;
+    double* s_nyq = s_mn + n_mn;
+    const int tid = threadIdx.x;
+    const int pts_per_surface = p.nalpha * p.nl;
+    const int tiles_per_surface = (pts_per_surface + GEO_THREADS - 1) / GEO_THREADS;
+    unsigned parity = 0;
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+
+    for (int js = blockIdx.y; js < p.ns; js += gridDim.y) {
+        // ---- stage this surface's packed tables in shared memory (TMA bulk copy)
+        __syncthreads();                       // everyone is done with the previous surface's tables
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, (unsigned)((n_mn + n_nyq) * sizeof(double)));
+            tma_bulk_g2s(s_mn, p.pk_mn + (size_t)js * n_mn, (unsigned)(n_mn * sizeof(double)), bar);
+            tma_bulk_g2s(s_nyq, p.pk_nyq + (size_t)js * n_nyq, (unsigned)(n_nyq * sizeof(double)), bar);
+        }
+        const double* sc = p.scal + (size_t)js * IBS_NSCAL;
+        const double s_val = sc[0], iota = sc[1], d_iota = sc[2], dpds = sc[3], shat = sc[4];
+        mbar_wait(bar, parity);
+        parity ^= 1;
+
+        for (int tile = blockIdx.x; tile < tiles_per_surface; tile += gridDim.x) {
+            const int pt = tile * GEO_THREADS + tid;
+            if (pt >= pts_per_surface) continue;
+            const int ja = pt / p.nl, jl = pt - ja * p.nl;
+            const double al = p.alpha_per_surface ? p.alpha[(size_t)js * p.nalpha + ja] : p.alpha[ja];
+            const double theta_p = p.theta[jl];
+            const double phi = p.phi_center + (theta_p - al) / iota;            // utils.py:373
+
+            // cos/sin(k nfp phi), k = 0..NT
+            double cn[NT + 1], sn[NT + 1];
+            cn[0] = 1.0; sn[0] = 0.0;
+            if (NT > 0) {
+                sincos((double)p.nfp * phi, &sn[1], &cn[1]);
+#pragma unroll
+                for (int k = 2; k <= NT; ++k) {
+                    cn[k] = fma(cn[k - 1], cn[1], -(sn[k - 1] * sn[1]));
+                    sn[k] = fma(sn[k - 1], cn[1], cn[k - 1] * sn[1]);
+                }
+            }
+            // ---- Newton for theta_vmec:  th + sum_m [ sin(m th) A_m - cos(m th) B_m ] = theta_p
+            double Am[NT1 > 0 ? MAX_M_NEWTON : 1], Bm[NT1 > 0 ? MAX_M_NEWTON : 1];
+            if (NT1 > 0) {
+                for (int m = 0; m < p.M1; ++m) {
+                    const double* row = s_mn + (size_t)m * W1 * ROW_MN;
+                    double a = 0.0, b = 0.0;
+#pragma unroll
+                    for (int q = 0; q < W1; ++q) {
+                        const double l = row[q * ROW_MN + 6];
+                        const int k = q - NT1;
+                        a = fma(l, cn[k < 0 ? -k : k], a);
+                        b = (k < 0) ? fma(-l, sn[-k], b) : fma(l, sn[k], b);
+                    }
+                    Am[m] = a; Bm[m] = b;
+                }
+            }
+            double th = theta_p;
+            int nit = 0; bool ok = false;
+            for (nit = 1; nit <= 25; ++nit) {
+                double s1, c1;
+                sincos(th, &s1, &c1);
+                double cm = 1.0, sm = 0.0, fsum = 0.0, dsum = 0.0;
+                for (int m = 0; m < p.M1; ++m) {
+                    const double a = (NT1 > 0) ? Am[m] : s_mn[(size_t)m * ROW_MN + 6];
+                    const double b = (NT1 > 0) ? Bm[m] : 0.0;
+                    fsum = fma(sm, a, fsum); fsum = fma(-cm, b, fsum);
+                    const double dm = (double)m;
+                    dsum = fma(dm * cm, a, dsum); dsum = fma(dm * sm, b, dsum);
+                    const double cnx = fma(cm, c1, -(sm * s1));
+                    sm = fma(sm, c1, cm * s1);
+                    cm = cnx;
+                }
+                const double res = (th + fsum) - theta_p;
+                const double dth = res / (1.0 + dsum);
+                th -= dth;
+                if (fabs(dth) <= 4.5e-16 * fmax(1.0, fabs(th))) { ok = true; break; }
+            }
+            // ---- mode sums (utils.py:420-468)
+            double s1, c1;
+            sincos(th, &s1, &c1);
+            double R = 0, R_s = 0, R_t = 0, R_p = 0, Z_s = 0, Z_t = 0, Z_p = 0, L_s = 0, L_t = 0, L_p = 0;
+            {
+                double cm = 1.0, sm = 0.0;
+                for (int m = 0; m < p.M1; ++m) {
+                    const double* row = s_mn + (size_t)m * W1 * ROW_MN;
+                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0, a9 = 0;
+#pragma unroll
+                    for (int q = 0; q < W1; ++q) {
+                        const int k = q - NT1, ak = k < 0 ? -k : k;
+                        double ca, sa;
+                        if (k >= 0) angle<1>(cm, sm, cn[ak], sn[ak], ca, sa);
+                        else angle<-1>(cm, sm, cn[ak], sn[ak], ca, sa);
+                        const double2 v0 = *reinterpret_cast<const double2*>(row + q * ROW_MN + 0);   // r, n r
+                        const double2 v1 = *reinterpret_cast<const double2*>(row + q * ROW_MN + 2);   // r_s, z
+                        const double2 v2 = *reinterpret_cast<const double2*>(row + q * ROW_MN + 4);   // n z, z_s
+                        const double2 v3 = *reinterpret_cast<const double2*>(row + q * ROW_MN + 6);   // l, n l
+                        const double v4 = row[q * ROW_MN + 8];                                          // l_s
+                        a0 = fma(v0.x, ca, a0);   // sum r cos
+                        a1 = fma(v0.x, sa, a1);   // sum r sin
+                        a2 = fma(v0.y, sa, a2);   // sum n r sin
+                        a3 = fma(v1.x, ca, a3);   // sum r_s cos
+                        a4 = fma(v1.y, ca, a4);   // sum z cos
+                        a5 = fma(v2.x, ca, a5);   // sum n z cos
+                        a6 = fma(v2.y, sa, a6);   // sum z_s sin
+                        a7 = fma(v3.x, ca, a7);   // sum l cos
+                        a8 = fma(v3.y, ca, a8);   // sum n l cos
+                        a9 = fma(v4, sa, a9);     // sum l_s sin
+                    }
+                    const double dm = (double)m;
+                    R += a0; R_t = fma(-dm, a1, R_t); R_p += a2; R_s += a3;
+                    Z_t = fma(dm, a4, Z_t); Z_p -= a5; Z_s += a6;
+                    L_t = fma(dm, a7, L_t); L_p -= a8; L_s += a9;
+                    const double cnx = fma(cm, c1, -(sm * s1));
+                    sm = fma(sm, c1, cm * s1);
+                    cm = cnx;
+                }
+            }
+            double sqrtg = 0, B = 0, B_s = 0, B_t = 0, B_p = 0, Bsup_p = 0, Bsub_s = 0, Bsub_t = 0, Bsub_p = 0;
+            {
+                double cm = 1.0, sm = 0.0;
+                for (int m = 0; m < p.M2; ++m) {
+                    const double* row = s_nyq + (size_t)m * W2 * ROW_NYQ;
+                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
+#pragma unroll
+                    for (int q = 0; q < W2; ++q) {
+                        const int k = q - NT2, ak = k < 0 ? -k : k;
+                        double ca, sa;
+                        if (k >= 0) angle<1>(cm, sm, cn[ak], sn[ak], ca, sa);
+                        else angle<-1>(cm, sm, cn[ak], sn[ak], ca, sa);
+                        const double2 v0 = *reinterpret_cast<const double2*>(row + q * ROW_NYQ + 0);  // g, b
+                        const double2 v1 = *reinterpret_cast<const double2*>(row + q * ROW_NYQ + 2);  // n b, b_s
+                        const double2 v2 = *reinterpret_cast<const double2*>(row + q * ROW_NYQ + 4);  // bsupv, bsubs
+                        const double2 v3 = *reinterpret_cast<const double2*>(row + q * ROW_NYQ + 6);  // bsubu, bsubv
+                        a0 = fma(v0.x, ca, a0);   // sqrt g
+                        a1 = fma(v0.y, ca, a1);   // B
+                        a2 = fma(v0.y, sa, a2);   // sum b sin
+                        a3 = fma(v1.x, sa, a3);   // sum n b sin
+                        a4 = fma(v1.y, ca, a4);   // dB/ds
+                        a5 = fma(v2.x, ca, a5);   // B^phi
+                        a6 = fma(v2.y, sa, a6);   // B_s
+                        a7 = fma(v3.x, ca, a7);   // B_theta
+                        a8 = fma(v3.y, ca, a8);   // B_phi
+                    }
+                    const double dm = (double)m;
+                    sqrtg += a0; B += a1; B_t = fma(-dm, a2, B_t); B_p += a3; B_s += a4;
+                    Bsup_p += a5; Bsub_s += a6; Bsub_t += a7; Bsub_p += a8;
+                    const double cnx = fma(cm, c1, -(sm * s1));
+                    sm = fma(sm, c1, cm * s1);
+                    cm = cnx;
+                }
+            }
+            // ---- Cartesian dual basis (utils.py:480-508)
+            double sp, cp;
+            sincos(phi, &sp, &cp);
+            const double X_t = R_t * cp, X_p = R_p * cp - R * sp, X_s = R_s * cp;
+            const double Y_t = R_t * sp, Y_p = R_p * sp + R * cp, Y_s = R_s * sp;
+            const double isg = 1.0 / sqrtg;
+            const double gsx = (Y_t * Z_p - Z_t * Y_p) * isg, gsy = (Z_t * X_p - X_t * Z_p) * isg, gsz = (X_t * Y_p - Y_t * X_p) * isg;
+            const double gtx = (Y_p * Z_s - Z_p * Y_s) * isg, gty = (Z_p * X_s - X_p * Z_s) * isg, gtz = (X_p * Y_s - Y_p * X_s) * isg;
+            const double gpx = (Y_s * Z_t - Z_s * Y_t) * isg, gpy = (Z_s * X_t - X_s * Z_t) * isg, gpz = (X_s * Y_t - Y_s * X_t) * isg;
+            // grad psi, grad alpha (utils.py:515-538)
+            const double psi_e = p.psi_e;
+            const double a_s = L_s - (phi - p.phi_center) * d_iota;
+            const double a_t = 1.0 + L_t, a_p = -iota + L_p;
+            const double gax = a_s * gsx + (a_t * gtx + a_p * gpx);
+            const double gay = a_s * gsy + (a_t * gty + a_p * gpy);
+            const double gaz = a_s * gsz + (a_t * gtz + a_p * gpz);
+            const double gqx = gsx * psi_e, gqy = gsy * psi_e, gqz = gsz * psi_e;
+            // drifts (utils.py:603-618, 646-650)
+            const double lpi = L_p - iota;
+            const double BxgB_ga = (Bsub_s * B_t * lpi + Bsub_t * B_p * a_s + Bsub_p * B_s * a_t - Bsub_p * B_t * a_s -
+                                    Bsub_t * B_s * lpi - Bsub_s * B_p * a_t) * isg;
+            const double ga_ga = gax * gax + gay * gay + gaz * gaz;
+            const double ga_gq = gax * gqx + gay * gqy + gaz * gqz;
+            const double gq_gq = gqx * gqx + gqy * gqy + gqz * gqz;
+            const double BxgB_gq = (Bsub_t * B_p - Bsub_p * B_t) * isg * psi_e;
+            // GS2 normalisations (utils.py:662-720)
+            const double L_ref = p.L_ref, B_ref = 2.0 * fabs(psi_e) / (L_ref * L_ref);
+            const double sgn = (psi_e > 0.0) ? 1.0 : ((psi_e < 0.0) ? -1.0 : 0.0);
+            const double sqrt_s = sqrt(s_val);
+            const double B3 = B * B * B;
+            const double mu0 = 4.0 * 3.141592653589793 * 1.0e-7;
+            const double bmag = B / B_ref;
+            const double gradpar = L_ref * (iota * Bsup_p) / B;
+            const double gds2 = ga_ga * L_ref * L_ref * s_val;
+            const double gds21 = ga_gq * shat / B_ref;
+            const double gds22 = gq_gq * shat * shat / (L_ref * L_ref * B_ref * B_ref * s_val);
+            const double gbdrift = -1.0 * 2.0 * B_ref * L_ref * L_ref * sqrt_s * BxgB_ga / B3 * sgn;
+            const double gbdrift0 = -1.0 * BxgB_gq * 2.0 * shat / (B3 * sqrt_s) * sgn;
+            const double cvdrift = gbdrift - 2.0 * B_ref * L_ref * L_ref * sqrt_s * mu0 * dpds * sgn / (psi_e * B * B);
+
+            const size_t line = (size_t)js * p.nalpha + ja;
+            double* o = p.base_out + line * IBS_NBASE * p.nl + jl;
+            o[(size_t)IBS_BASE_BMAG * p.nl] = bmag;
+            o[(size_t)IBS_BASE_GRADPAR * p.nl] = gradpar;
+            o[(size_t)IBS_BASE_CVDRIFT * p.nl] = cvdrift;
+            o[(size_t)IBS_BASE_CVDRIFT0 * p.nl] = gbdrift0;      // cvdrift0 = gbdrift0 (utils.py:720)
+            o[(size_t)IBS_BASE_GDS2 * p.nl] = gds2;
+            o[(size_t)IBS_BASE_GDS21 * p.nl] = gds21;
+            o[(size_t)IBS_BASE_GDS22 * p.nl] = gds22;
+            o[(size_t)IBS_BASE_GBDRIFT * p.nl] = gbdrift;
+            if (p.theta_vmec_out) p.theta_vmec_out[line * p.nl + jl] = th;
+            if (p.info_out) atomicMax(p.info_out + line, nit | (ok ? 0 : (1 << 16)));
+        }
+    }
+}
+
+// dPdrho = -1.0 * 0.5 * mean((cvdrift - gbdrift) * bmag**2)   (ball_scan.py:262); one warp per line.
+__global__ void dpdrho_kernel(const double* __restrict__ base, int nlines, int nl, double* __restrict__ out) {
+    const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (line >= nlines) return;
+    const int lane = threadIdx.x & 31;
+    const double* b = base + (size_t)line * IBS_NBASE * nl;
+    double acc = 0.0;
+    for (int j = lane; j < nl; j += 32) {
+        const double bm = b[(size_t)IBS_BASE_BMAG * nl + j];
+        acc += __dmul_rn(__dsub_rn(b[(size_t)IBS_BASE_CVDRIFT * nl + j], b[(size_t)IBS_BASE_GBDRIFT * nl + j]), __dmul_rn(bm, bm));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[line] = -1.0 * 0.5 * (acc / (double)nl);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+template <int NT1, int NT2>
+static int launch_geometry(const GeoParams& p, cudaStream_t st) {
+    auto kern = geometry_kernel<NT1, NT2>;
+    const size_t smem = 16 + ((size_t)p.M1 * (2 * NT1 + 1) * ROW_MN + (size_t)p.M2 * (2 * NT2 + 1) * ROW_NYQ) * sizeof(double);
+    if (smem > 200 * 1024) { set_error("Fourier tables of one surface do not fit in shared memory"); return IBS_ERR_UNSUPPORTED; }
+    static bool configured = false;
+    if (!configured) {
+        IBS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    int per_sm = 0;
+    IBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GEO_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int tiles = (p.nalpha * p.nl + GEO_THREADS - 1) / GEO_THREADS;
+    const long long slots = (long long)num_sms() * per_sm;
+    // y = surfaces (each CTA keeps one surface's tables resident), x = tiles of that surface
+    int gy = p.ns, gx = (int)((slots + gy - 1) / gy);
+    if (gx > tiles) gx = tiles;
+    if (gx < 1) gx = 1;
+    if (gy > 65535) gy = 65535;
+    kern<<<dim3(gx, gy), GEO_THREADS, smem, st>>>(p);
+    IBS_CUDA_CHECK(cudaGetLastError());
+    return IBS_OK;
+}
+
+static int gcd_int(int a, int b) { a = std::abs(a); b = std::abs(b); while (b) { int t = a % b; a = b; b = t; } return a; }
+
+int geometry_dispatch(const double* tab_mn, const double* tab_nyq, const double* scal,
+                      const double* xm, const double* xn, const double* xm_nyq, const double* xn_nyq,
+                      int ns, int mnmax, int mnmax_nyq, double phiedge, double aminor_p,
+                      const double* alpha, int nalpha, int alpha_per_surface, const double* theta, int nl,
+                      double phi_center, double* base_out, double* dPdrho_out, double* theta_vmec_out,
+                      int* info_out, cudaStream_t st) {
+    // ---- mode bookkeeping (host): toroidal stride, extents, dense-grid index of every mode
+    int nfp = 0, mmax1 = 0, mmax2 = 0;
+    for (int k = 0; k < mnmax; ++k) { nfp = gcd_int(nfp, (int)std::lround(xn[k])); mmax1 = std::max(mmax1, (int)std::lround(xm[k])); }
+    for (int k = 0; k < mnmax_nyq; ++k) { nfp = gcd_int(nfp, (int)std::lround(xn_nyq[k])); mmax2 = std::max(mmax2, (int)std::lround(xm_nyq[k])); }
+    if (nfp == 0) nfp = 1;
+    int nt1 = 0, nt2 = 0;
+    std::vector<int> h_idx(2 * (size_t)(mnmax + mnmax_nyq));
+    int* m1 = h_idx.data(); int* n1 = m1 + mnmax; int* m2 = n1 + mnmax; int* n2 = m2 + mnmax_nyq;
+    for (int k = 0; k < mnmax; ++k) {
+        m1[k] = (int)std::lround(xm[k]); n1[k] = (int)std::lround(xn[k]) / nfp;
+        IBS_REQUIRE(m1[k] >= 0 && std::fabs(xm[k] - m1[k]) < 1e-9 && std::fabs(xn[k] - (double)n1[k] * nfp) < 1e-9, "non-integer mode numbers");
+        nt1 = std::max(nt1, std::abs(n1[k]));
+    }
+    for (int k = 0; k < mnmax_nyq; ++k) {
+        m2[k] = (int)std::lround(xm_nyq[k]); n2[k] = (int)std::lround(xn_nyq[k]) / nfp;
+        IBS_REQUIRE(m2[k] >= 0 && std::fabs(xm_nyq[k] - m2[k]) < 1e-9 && std::fabs(xn_nyq[k] - (double)n2[k] * nfp) < 1e-9, "non-integer mode numbers");
+        nt2 = std::max(nt2, std::abs(n2[k]));
+    }
+    int NT1, NT2;
+    if (nt1 == 0 && nt2 == 0) { NT1 = 0; NT2 = 0; }
+    else if (nt1 <= 6 && nt2 <= 8) { NT1 = 6; NT2 = 8; }
+    else if (nt1 <= 11 && nt2 <= 13) { NT1 = 11; NT2 = 13; }
+    else if (nt1 <= 16 && nt2 <= 18) { NT1 = 16; NT2 = 18; }
+    else { set_error("toroidal mode range |n|/nfp > 18 is not supported"); return IBS_ERR_UNSUPPORTED; }
+    const int M1 = mmax1 + 1, M2 = mmax2 + 1, W1 = 2 * NT1 + 1, W2 = 2 * NT2 + 1;
+    if (NT1 > 0 && M1 > MAX_M_NEWTON) { set_error("mpol too large for a 3-D equilibrium"); return IBS_ERR_UNSUPPORTED; }
+
+    // ---- workspace: packed tables (stream-ordered allocation) + cached device copy of the mode indices
+    const size_t n_mn = (size_t)ns * M1 * W1 * ROW_MN, n_nyq = (size_t)ns * M2 * W2 * ROW_NYQ;
+    double* pk = nullptr; int* d_idx = nullptr;
+    {
+        // The mode layout of an equilibrium family never changes between calls: keep the last one on
+        // the device so steady-state calls issue no host->device copy and no host synchronisation.
+        static std::mutex mu;
+        static std::vector<int> cached; static int* cached_dev = nullptr; static int cached_device = -1;
+        std::lock_guard<std::mutex> lk(mu);
+        int dev = 0; IBS_CUDA_CHECK(cudaGetDevice(&dev));
+        if (!(cached_dev && cached_device == dev && cached == h_idx)) {
+            if (cached_dev && cached_device == dev) { IBS_CUDA_CHECK(cudaStreamSynchronize(st)); cudaFree(cached_dev); }
+            cached_dev = nullptr;
+            IBS_CUDA_CHECK(cudaMalloc((void**)&cached_dev, h_idx.size() * sizeof(int)));
+            IBS_CUDA_CHECK(cudaMemcpy(cached_dev, h_idx.data(), h_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+            cached = h_idx; cached_device = dev;
+        }
+        d_idx = cached_dev;
+    }
+    IBS_CUDA_CHECK(cudaMallocAsync((void**)&pk, (n_mn + n_nyq) * sizeof(double), st));
+    IBS_CUDA_CHECK(cudaMemsetAsync(pk, 0, (n_mn + n_nyq) * sizeof(double), st));
+    pack_mn_kernel<<<dim3((mnmax + 127) / 128, ns), 128, 0, st>>>(tab_mn, d_idx, d_idx + mnmax, ns, mnmax, M1, W1, NT1, nfp, pk);
+    pack_nyq_kernel<<<dim3((mnmax_nyq + 127) / 128, ns), 128, 0, st>>>(tab_nyq, d_idx + 2 * mnmax, d_idx + 2 * mnmax + mnmax_nyq, ns,
+                                                                     mnmax_nyq, M2, W2, NT2, nfp, pk + n_mn);
+    IBS_CUDA_CHECK(cudaGetLastError());
+
+    GeoParams p;
+    p.pk_mn = pk; p.pk_nyq = pk + n_mn; p.scal = scal;
+    p.alpha = alpha; p.nalpha = nalpha; p.alpha_per_surface = alpha_per_surface;
+    p.theta = theta; p.nl = nl; p.ns = ns; p.M1 = M1; p.M2 = M2; p.nfp = nfp;
+    p.phi_center = phi_center; p.psi_e = -phiedge / (2.0 * 3.141592653589793); p.L_ref = aminor_p;
+    p.base_out = base_out; p.theta_vmec_out = theta_vmec_out; p.info_out = info_out;
+    if (info_out) IBS_CUDA_CHECK(cudaMemsetAsync(info_out, 0, (size_t)ns * nalpha * sizeof(int), st));
+    int rc;
+    if (NT1 == 0) rc = launch_geometry<0, 0>(p, st);
+    else if (NT1 == 6) rc = launch_geometry<6, 8>(p, st);
+    else if (NT1 == 11) rc = launch_geometry<11, 13>(p, st);
+    else rc = launch_geometry<16, 18>(p, st);
+    if (rc == IBS_OK && dPdrho_out) {
+        const int nlines = ns * nalpha;
+        dpdrho_kernel<<<(nlines + 3) / 4, 128, 0, st>>>(base_out, nlines, nl, dPdrho_out);
+        if (cudaGetLastError() != cudaSuccess) rc = IBS_ERR_CUDA;
+    }
+    cudaFreeAsync(pk, st);
+    return rc;
+}
+
+}  // namespace ibs

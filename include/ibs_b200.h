@@ -1,0 +1,167 @@
+/* ibs_b200.h -- C ABI of the B200-native ideal-ballooning hot path.
+ *
+ * The reference (rahulgaur104/ideal-ballooning-solver) is pure Python and has no FFI layer; the
+ * boundary this library sits behind is the set of Python call signatures that ball_scan.py reaches
+ * through `from utils import *` (ball_scan.py:19).  Each entry point below names the reference
+ * interface it replaces (file:line under /root/reference).  INTEGRATION.md shows the ctypes stub a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - all arrays are fp64, row-major, caller-allocated; pointers are DEVICE pointers unless the
+ *     function name ends in `_host`;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), does not synchronise
+ *     the host and keeps no global mutable state except the thread-local error string;
+ *   - return value 0 = OK, non-zero = error (see ibs_last_error());
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Grid convention: N = number of theta points of a field line (the reference's `ntheta`,
+ * ball_scan.py:203-208), M = N-2 interior unknowns (Dirichlet ends, utils.py:1607-1608).
+ */
+#ifndef IBS_B200_H
+#define IBS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IBS_OK 0
+#define IBS_ERR_INVALID 1   /* bad argument                                   */
+#define IBS_ERR_CUDA 2      /* CUDA runtime error (message in ibs_last_error) */
+#define IBS_ERR_UNSUPPORTED 3
+
+/* Layout of the per-field-line "base" arrays produced by ibs_geometry_batch and consumed by the
+ * solver/adjoint entry points: base[line][IBS_NBASE][N].  These are exactly the eight quantities the
+ * reference's hot path reads from the vmec_fieldlines Struct (ball_scan.py:254-261, utils.py:1649-1656). */
+#define IBS_BASE_BMAG 0
+#define IBS_BASE_GRADPAR 1     /* gradpar_theta_pest */
+#define IBS_BASE_CVDRIFT 2
+#define IBS_BASE_CVDRIFT0 3
+#define IBS_BASE_GDS2 4
+#define IBS_BASE_GDS21 5
+#define IBS_BASE_GDS22 6
+#define IBS_BASE_GBDRIFT 7
+#define IBS_NBASE 8
+
+/* rows of the per-surface Fourier tables (utils.py:318-357) */
+#define IBS_TAB_MN_ROWS 6      /* rmnc zmns lmns d_rmnc_d_s d_zmns_d_s d_lmns_d_s               */
+#define IBS_TAB_NYQ_ROWS 7     /* gmnc bmnc d_bmnc_d_s bsupvmnc bsubsmns bsubumnc bsubvmnc      */
+#define IBS_NSCAL 8            /* s iota d_iota_d_s d_pressure_d_s shat pressure (2 spare)      */
+
+/* bits of the per-solve info word written by the solver: info = iterations | flags << 16 */
+#define IBS_FLAG_NOT_CONVERGED 1   /* iteration cap hit                                          */
+#define IBS_FLAG_BAD_INPUT 2       /* non-finite input, or g <= 0 / f <= 0 somewhere            */
+#define IBS_FLAG_SIGMA_NOT_MAX 4   /* eigenvalue nearest sigma (ARPACK semantics) is not lambda_max */
+
+int ibs_version(void);
+const char* ibs_last_error(void);
+/* number of SMs / compute capability of the current device (0 on success) */
+int ibs_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K1: field-line geometry ------------------------------------------------------------------
+ * Batched vmec_fieldlines(vs, s, alpha, theta1d=theta) (utils.py:161-864) restricted to the eight
+ * arrays the ballooning path reads, for ns surfaces x nalpha field lines x nl points:
+ * theta_vmec root solve (utils.py:391-416), the 19 Fourier mode sums (utils.py:420-468), the
+ * Cartesian dual basis / drifts (utils.py:474-658) and the GS2 normalisations (utils.py:662-720).
+ * Also forms dPdrho = -0.5*mean((cvdrift-gbdrift)*bmag^2) per line (ball_scan.py:262).
+ *   tab_mn  [ns][6][mnmax], tab_nyq [ns][7][mnmax_nyq], scal [ns][8]: per-surface tables
+ *   xm,xn [mnmax], xm_nyq,xn_nyq [mnmax_nyq]: mode numbers (xn already multiplied by nfp) -- HOST pointers
+ *          (metadata: the library derives the dense (m, n) layout from them and caches it on the device)
+ *   alpha: [nalpha] shared by all surfaces (alpha_per_surface = 0) or [ns][nalpha] (= 1)
+ *   theta [nl]: theta_pest grid; phi = phi_center + (theta - alpha)/iota (utils.py:373)
+ *   base_out [ns*nalpha][8][nl]; dPdrho_out [ns*nalpha]; theta_vmec_out [ns*nalpha][nl] or NULL;
+ *   info_out [ns*nalpha] or NULL: max Newton iterations used | (not converged) << 16              */
+int ibs_geometry_batch(const double* tab_mn, const double* tab_nyq, const double* scal,
+                       const double* xm, const double* xn, const double* xm_nyq, const double* xn_nyq,
+                       int ns, int mnmax, int mnmax_nyq, double phiedge, double aminor_p,
+                       const double* alpha, int nalpha, int alpha_per_surface,
+                       const double* theta, int nl, double phi_center,
+                       double* base_out, double* dPdrho_out, double* theta_vmec_out, int* info_out,
+                       void* stream);
+
+/* ---- K2+K3: discretisation + lambda_max + eigenfunction -------------------------------------------
+ * Batched gamma_ball_full (utils.py:1550-1624): g, c, f -> half-grid g, second-order finite
+ * differences, Dirichlet ends (utils.py:1564-1592) -> largest eigenvalue and eigenvector of
+ * A = F^-1 (D g D + c) -> X = v / max|v| (utils.py:1605), dX stencil (utils.py:1610-1616), Simpson
+ * Rayleigh quotient gam = int(-g dX^2 + c X^2) / int(f X^2) (utils.py:1618-1621).
+ *   g, c, f [nsolve][N] on a uniform theta grid of spacing h (the reference's np.diff(theta_half)[2])
+ *   lam0   [nsolve] or NULL: optional starting shifts (any value is safe)
+ *   sigma  [nsolve] or NULL: if given, IBS_FLAG_SIGMA_NOT_MAX is raised when ARPACK's
+ *          "eigenvalue nearest sigma" (utils.py:1597) would not be lambda_max
+ *   lam_out [nsolve]: the reference's returned `gam`; lam_matrix_out [nsolve] or NULL: lambda_max of
+ *          the pencil itself; X_out, dX_out [nsolve][N] or NULL (X >= 0, max X = 1);
+ *   info_out [nsolve] or NULL.                                                                        */
+int ibs_solve_gcf_batch(const double* g, const double* c, const double* f, int nsolve, int N, double h,
+                        const double* lam0, const double* sigma,
+                        double* lam_out, double* lam_matrix_out, double* X_out, double* dX_out,
+                        int* info_out, void* stream);
+
+/* Same solve, but the coefficients are formed on the fly from the base arrays of a field line
+ * (ball_scan.py:267-268, utils.py:1560-1562):
+ *   cvdrift_fth = cvdrift + theta0 cvdrift0,  gds2_fth = gds2 + 2 theta0 gds21 + theta0^2 gds22,
+ *   g = |gradpar| gds2_fth / bmag,  c = -dPdrho cvdrift_fth / (|gradpar| bmag),
+ *   f = gds2_fth / (bmag^3 |gradpar|).
+ *   base [nline][8][N], dPdrho [nline], theta0 [nsolve];
+ *   line_of_solve [nsolve] or NULL (then line = solve / nth0, i.e. theta0 fastest).
+ *   g_out, c_out, f_out [nsolve][N] or NULL: the coefficient arrays gamma_ball_full returns.      */
+int ibs_solve_base_batch(const double* base, const double* dPdrho, const double* theta0,
+                         const int* line_of_solve, int nth0, int nsolve, int N, double h,
+                         const double* lam0, const double* sigma,
+                         double* lam_out, double* lam_matrix_out, double* X_out, double* dX_out,
+                         double* g_out, double* c_out, double* f_out, int* info_out, void* stream);
+
+/* ---- K4: adjoint (Hellmann-Feynman) gradient -----------------------------------------------------
+ * d(lam)/dp = [ int c_p X^2 - int g_p dX^2 - lam int f_p X^2 ] / int f X^2 (utils.py:1666-1680,
+ * 1716-1725) for nparam perturbation triples per solve.
+ *   lam [nsolve]; X, dX, f [nsolve][N]; g_p, c_p, f_p [nsolve][nparam][N]; grad_out [nsolve][nparam] */
+int ibs_adjoint_batch(const double* lam, const double* X, const double* dX, const double* f,
+                      const double* g_p, const double* c_p, const double* f_p,
+                      int nsolve, int nparam, int N, double* grad_out, void* stream);
+
+/* Per-point sensitivities of lam to the coefficient arrays (what a chained adjoint consumes):
+ *   dlam/dg_j = -w_j dX_j^2 / Y1,  dlam/dc_j = w_j X_j^2 / Y1,  dlam/df_j = -lam w_j X_j^2 / Y1,
+ * w = Simpson weights, Y1 = int f X^2.  Outputs [nsolve][N] each (any may be NULL).              */
+int ibs_adjoint_sensitivities(const double* lam, const double* X, const double* dX, const double* f,
+                              int nsolve, int N, double* dlam_dg, double* dlam_dc, double* dlam_df,
+                              void* stream);
+
+/* Batched obj_w_grad (utils.py:1632-1728).  For each of npoint (alpha, theta0) points the caller
+ * supplies the base arrays of the three field lines alpha-del/2, alpha, alpha+del/2
+ * (base3 [npoint][3][8][N], dPdrho3 [npoint][3]); the centre line is solved, d/dtheta0 is analytic
+ * (utils.py:1669-1680) and d/dalpha is the central difference of (g, c, f) (utils.py:1707-1725).
+ *   val_out [npoint] = -lam; grad_out [npoint][2] = (-dlam/dalpha, -dlam/dtheta0) (utils.py:1728);
+ *   lam0 [npoint] or NULL; X_out, dX_out [npoint][N] or NULL; info_out [npoint] or NULL.          */
+int ibs_obj_w_grad_batch(const double* base3, const double* dPdrho3, const double* theta0,
+                         int npoint, int N, double h, double del_alpha, const double* lam0,
+                         double* val_out, double* grad_out, double* X_out, double* dX_out,
+                         int* info_out, void* stream);
+
+/* ---- scan: per-surface arg-max with the reference's guards (ball_scan.py:279-295) ----------------
+ * gamma [ns][ngrid] (row-major (alpha, theta0) grid flattened).  For each surface:
+ * max == 0.0 -> idx = -1 (alpha_guess = theta0_guess = 0, sigma0 = 0.05); otherwise the FIRST flat
+ * index attaining the maximum (np.where(...)[k][0]); sigma0 = 1.3 |max| + 0.05.
+ *   val_out [ns], idx_out [ns], sigma0_out [ns] or NULL                                            */
+int ibs_scan_argmax(const double* gamma, int ns, int ngrid, double* val_out, int* idx_out,
+                    double* sigma0_out, void* stream);
+
+/* ---- marginal-stability classifier ---------------------------------------------------------------
+ * Sturm/Newcomb node count of the discretised ballooning operator at a given lam (the s-alpha test
+ * of the reference shoots at lam = 0, tests/shifted-circle-s-alpha/bishop_ball_s-alpha.py:90-115):
+ * count_out[i] = number of eigenvalues of the pencil greater than lam[i]; unstable <=> count(0) > 0. */
+int ibs_count_above_batch(const double* g, const double* c, const double* f, int nsolve, int N, double h,
+                          const double* lam, int* count_out, void* stream);
+
+/* ---- end-to-end host entry point -----------------------------------------------------------------
+ * Coarse scan of ball_scan.py:248-295 for ns surfaces with HOST buffers: copies the tables to the
+ * device, runs K1 (ns x nalpha lines), K3 (ns x nalpha x nth0 solves) and the arg-max, and copies
+ * gamma [ns][nalpha][nth0] and the per-surface (val, idx, sigma0) back.  Synchronous.              */
+int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* scal,
+                  const double* xm, const double* xn, const double* xm_nyq, const double* xn_nyq,
+                  int ns, int mnmax, int mnmax_nyq, double phiedge, double aminor_p,
+                  const double* alpha, int nalpha, const double* theta0, int nth0,
+                  const double* theta, int nl, double h,
+                  double* gamma_out, double* val_out, int* idx_out, double* sigma0_out, int* nbad_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IBS_B200_H */
