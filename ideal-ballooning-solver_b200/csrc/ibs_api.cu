@@ -83,8 +83,9 @@ int ibs_geometry_batch(const double* tab_mn, const double* tab_nyq, const double
 int ibs_solve_gcf_batch(const double* g, const double* c, const double* f, int nsolve, int N, double h,
                         const double* lam0, const double* sigma, double* lam_out, double* lam_matrix_out,
                         double* X_out, double* dX_out, int* info_out, void* stream) {
-    IBS_REQUIRE(g && c && f && lam_out, "null pointer");
     IBS_REQUIRE(nsolve >= 0 && N >= 3, "need nsolve >= 0 and N >= 3");
+    if (nsolve == 0) return IBS_OK;                 // empty batches are legal (and have null pointers)
+    IBS_REQUIRE(g && c && f && lam_out, "null pointer");
     IBS_REQUIRE(h > 0.0, "h must be positive");
     SolveParams p = blank_params();
     p.g = g; p.c = c; p.f = f; p.nsolve = nsolve; p.N = N; p.h = h; p.lam0 = lam0; p.sigma = sigma;
@@ -96,8 +97,9 @@ int ibs_solve_base_batch(const double* base, const double* dPdrho, const double*
                          int nth0, int nsolve, int N, double h, const double* lam0, const double* sigma,
                          double* lam_out, double* lam_matrix_out, double* X_out, double* dX_out, double* g_out,
                          double* c_out, double* f_out, int* info_out, void* stream) {
-    IBS_REQUIRE(base && dPdrho && theta0 && lam_out, "null pointer");
     IBS_REQUIRE(nsolve >= 0 && N >= 3, "need nsolve >= 0 and N >= 3");
+    if (nsolve == 0) return IBS_OK;
+    IBS_REQUIRE(base && dPdrho && theta0 && lam_out, "null pointer");
     IBS_REQUIRE(line_of_solve || nth0 >= 1, "need line_of_solve or nth0 >= 1");
     IBS_REQUIRE(h > 0.0, "h must be positive");
     SolveParams p = blank_params();
@@ -110,8 +112,9 @@ int ibs_solve_base_batch(const double* base, const double* dPdrho, const double*
 
 int ibs_count_above_batch(const double* g, const double* c, const double* f, int nsolve, int N, double h,
                           const double* lam, int* count_out, void* stream) {
-    IBS_REQUIRE(g && c && f && lam && count_out, "null pointer");
     IBS_REQUIRE(nsolve >= 0 && N >= 3 && h > 0.0, "bad sizes");
+    if (nsolve == 0) return IBS_OK;
+    IBS_REQUIRE(g && c && f && lam && count_out, "null pointer");
     SolveParams p = blank_params();
     p.g = g; p.c = c; p.f = f; p.nsolve = nsolve; p.N = N; p.h = h; p.lam_query = lam; p.count_out = count_out;
     return solve_dispatch(p, false, true, (cudaStream_t)stream);
@@ -120,24 +123,26 @@ int ibs_count_above_batch(const double* g, const double* c, const double* f, int
 int ibs_adjoint_batch(const double* lam, const double* X, const double* dX, const double* f, const double* g_p,
                       const double* c_p, const double* f_p, int nsolve, int nparam, int N, double* grad_out,
                       void* stream) {
-    IBS_REQUIRE(lam && X && dX && f && g_p && c_p && f_p && grad_out, "null pointer");
     IBS_REQUIRE(nsolve >= 0 && nparam >= 0 && N >= 3, "bad sizes");
+    if (nsolve == 0 || nparam == 0) return IBS_OK;
+    IBS_REQUIRE(lam && X && dX && f && g_p && c_p && f_p && grad_out, "null pointer");
     return launch_adjoint(lam, X, dX, f, g_p, c_p, f_p, nsolve, nparam, N, grad_out, (cudaStream_t)stream);
 }
 
 int ibs_adjoint_sensitivities(const double* lam, const double* X, const double* dX, const double* f, int nsolve,
                               int N, double* dlam_dg, double* dlam_dc, double* dlam_df, void* stream) {
-    IBS_REQUIRE(lam && X && dX && f, "null pointer");
     IBS_REQUIRE(nsolve >= 0 && N >= 3, "bad sizes");
+    if (nsolve == 0) return IBS_OK;
+    IBS_REQUIRE(lam && X && dX && f, "null pointer");
     return launch_sensitivity(lam, X, dX, f, nsolve, N, dlam_dg, dlam_dc, dlam_df, (cudaStream_t)stream);
 }
 
 int ibs_obj_w_grad_batch(const double* base3, const double* dPdrho3, const double* theta0, int npoint, int N,
                          double h, double del_alpha, const double* lam0, double* val_out, double* grad_out,
                          double* X_out, double* dX_out, int* info_out, void* stream) {
-    IBS_REQUIRE(base3 && dPdrho3 && theta0 && val_out && grad_out, "null pointer");
     IBS_REQUIRE(npoint >= 0 && N >= 3 && h > 0.0 && del_alpha != 0.0, "bad sizes");
     if (npoint == 0) return IBS_OK;
+    IBS_REQUIRE(base3 && dPdrho3 && theta0 && val_out && grad_out, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     // stream-ordered scratch: centre-line indices, lambda, and X / dX when the caller does not want them
     int* line = nullptr; double* lam = nullptr; double* Xw = nullptr; double* dXw = nullptr;

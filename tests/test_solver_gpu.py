@@ -127,7 +127,8 @@ def test_sizes_against_oracle(cuda_lib, N):
         fi = fu[1:-1]
         w, U = eigh_tridiagonal(diag, sup * np.sqrt(fi[:-1] / fi[1:]), select="i", select_range=(N - 3, N - 3))
         gam, X, dX = bo.postprocess(U[:, 0] / np.sqrt(fi), h, gu, cu, fu)
-        np.testing.assert_allclose(sol.lam_matrix[k].item(), w[0], rtol=1e-11, atol=1e-12)
+        # LAPACK's own eigenvalue error is ~eps*||S||; the flux-form recurrence is more accurate than that
+        np.testing.assert_allclose(sol.lam_matrix[k].item(), w[0], rtol=1e-11, atol=8 * 2.2e-16 * np.abs(diag).max())
         if N >= 9:
             np.testing.assert_allclose(sol.lam[k].item(), gam, rtol=1e-9, atol=1e-12)
             np.testing.assert_allclose(sol.X[k].cpu().numpy(), sign_normalise(X), rtol=0, atol=1e-7)
