@@ -32,7 +32,7 @@ SIGNATURES = {
     "ibs_scan_argmax": (c_int, [_D, c_int, c_int, _D, _I, _D, c_void_p]),
     "ibs_count_above_batch": (c_int, [_D, _D, _D, c_int, c_int, c_double, _D, _I, c_void_p]),
     "ibs_scan_host": (c_int, [_D, _D, _D, _D, _D, _D, _D, c_int, c_int, c_int, c_double, c_double,
-                              _D, c_int, _D, c_int, _D, c_int, c_double, _D, _D, _I, _D, _I]),
+                              _D, c_int, _D, c_int, _D, c_int, c_double, _D, _D, _I, _D, _D, _I]),
 }
 
 _lib = None

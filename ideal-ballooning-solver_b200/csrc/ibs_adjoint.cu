@@ -192,6 +192,21 @@ argmax_kernel(const double* __restrict__ gamma, int ngrid, double* __restrict__ 
     }
 }
 
+// X of each surface's arg-max solve (flat index 0 when the all-zero guard fired): [ns][N]
+__global__ void gather_best_kernel(const double* __restrict__ X, const int* __restrict__ idx, int ngrid, int N,
+                                   double* __restrict__ out) {
+    const int s = blockIdx.x;
+    const int k = idx[s] < 0 ? 0 : idx[s];
+    const double* src = X + ((size_t)s * ngrid + k) * N;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) out[(size_t)s * N + j] = src[j];
+}
+int launch_gather_best(const double* X, const int* idx, int ns, int ngrid, int N, double* out, cudaStream_t st) {
+    if (ns == 0) return IBS_OK;
+    gather_best_kernel<<<ns, 256, 0, st>>>(X, idx, ngrid, N, out);
+    IBS_CUDA_CHECK(cudaGetLastError());
+    return IBS_OK;
+}
+
 int launch_adjoint(const double* lam, const double* X, const double* dX, const double* f, const double* g_p,
                    const double* c_p, const double* f_p, int nsolve, int nparam, int N, double* grad,
                    cudaStream_t st) {

@@ -24,6 +24,7 @@ int launch_obj_grad(const double* base3, const double* dPdrho3, const double* th
                     double* grad, cudaStream_t st);
 int launch_centre_lines(int* line, int n, cudaStream_t st);
 int launch_argmax(const double* gamma, int ns, int ngrid, double* val, int* idx, double* sigma0, cudaStream_t st);
+int launch_gather_best(const double* X, const int* idx, int ns, int ngrid, int N, double* out, cudaStream_t st);
 
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
@@ -179,7 +180,7 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
                   int ns, int mnmax, int mnmax_nyq, double phiedge, double aminor_p,
                   const double* alpha, int nalpha, const double* theta0, int nth0,
                   const double* theta, int nl, double h,
-                  double* gamma_out, double* val_out, int* idx_out, double* sigma0_out, int* nbad_out) {
+                  double* gamma_out, double* val_out, int* idx_out, double* sigma0_out, double* xbest_out, int* nbad_out) {
     IBS_REQUIRE(tab_mn && tab_nyq && scal && alpha && theta0 && theta && gamma_out, "null pointer");
     IBS_REQUIRE(ns >= 1 && nalpha >= 1 && nth0 >= 1 && nl >= 3, "bad sizes");
     cudaStream_t st = nullptr;
@@ -192,7 +193,8 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
     const size_t o_tmn = take(b_tab_mn), o_tnq = take(b_tab_nyq), o_sc = take(b_scal), o_al = take((size_t)nalpha * 8),
                  o_th = take((size_t)nl * 8), o_t0 = take(nsolve * 8), o_base = take(nlines * IBS_NBASE * nl * 8),
                  o_dp = take(nlines * 8), o_gam = take(nsolve * 8), o_val = take((size_t)ns * 8), o_sig = take((size_t)ns * 8),
-                 o_idx = take((size_t)ns * 4), o_info = take(nsolve * 4);
+                 o_idx = take((size_t)ns * 4), o_info = take(nsolve * 4),
+                 o_X = take(xbest_out ? nsolve * nl * 8 : 0), o_xb = take(xbest_out ? (size_t)ns * nl * 8 : 0);
     char* d = nullptr;
     int rc = IBS_OK;
     std::vector<double> t0_rep(nsolve);
@@ -214,11 +216,17 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
         SolveParams p = blank_params();
         p.base = (double*)(d + o_base); p.dPdrho = (double*)(d + o_dp); p.theta0 = (double*)(d + o_t0); p.nth0 = nth0;
         p.nsolve = (int)nsolve; p.N = nl; p.h = h; p.lam_out = (double*)(d + o_gam); p.info_out = (int*)(d + o_info);
+        if (xbest_out) p.X_out = (double*)(d + o_X);
         rc = solve_dispatch(p, true, false, st);
         if (rc != IBS_OK) goto done;
     }
     rc = launch_argmax((double*)(d + o_gam), ns, nalpha * nth0, (double*)(d + o_val), (int*)(d + o_idx), (double*)(d + o_sig), st);
     if (rc != IBS_OK) goto done;
+    if (xbest_out) {
+        rc = launch_gather_best((double*)(d + o_X), (int*)(d + o_idx), ns, nalpha * nth0, nl, (double*)(d + o_xb), st);
+        if (rc != IBS_OK) goto done;
+        IBS_TRY(cudaMemcpyAsync(xbest_out, d + o_xb, (size_t)ns * nl * 8, cudaMemcpyDeviceToHost, st));
+    }
     IBS_TRY(cudaMemcpyAsync(gamma_out, d + o_gam, nsolve * 8, cudaMemcpyDeviceToHost, st));
     if (val_out) IBS_TRY(cudaMemcpyAsync(val_out, d + o_val, (size_t)ns * 8, cudaMemcpyDeviceToHost, st));
     if (idx_out) IBS_TRY(cudaMemcpyAsync(idx_out, d + o_idx, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));

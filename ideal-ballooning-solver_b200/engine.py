@@ -293,9 +293,11 @@ def scan_argmax(gamma):
     return val, idx, sig
 
 
-def scan_host(st: SurfaceTables, alpha, theta0, theta):
+def scan_host(st: SurfaceTables, alpha, theta0, theta, want_xbest: bool = False, out=None):
     """End-to-end coarse scan with HOST (numpy) buffers through ``ibs_scan_host``: H2D of the tables,
-    K1 + K3 + arg-max, D2H of the results.  Returns ``(gamma (ns, nalpha, nth0), val, idx, sigma0, nbad)``."""
+    K1 + K3 + arg-max, D2H of the results.  Returns ``(gamma (ns, nalpha, nth0), val, idx, sigma0, nbad)``
+    (+ ``xbest (ns, nl)``, the eigenfunction at each surface's maximum, when ``want_xbest``).  ``out`` may
+    carry preallocated (e.g. pinned) result arrays ``dict(gamma=, val=, idx=, sigma0=, xbest=)``."""
     _lib.require_cuda()
     lib = _lib.load()
     c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -303,14 +305,22 @@ def scan_host(st: SurfaceTables, alpha, theta0, theta):
     xm, xn, xmq, xnq = c(st.xm), c(st.xn), c(st.xm_nyq), c(st.xn_nyq)
     alpha, theta0, theta = c(alpha), c(theta0), c(theta)
     ns, na, nt, nl = tab_mn.shape[0], alpha.size, theta0.size, theta.size
-    gamma = np.empty((ns, na, nt))
-    val, sig = np.empty(ns), np.empty(ns)
-    idx = np.empty(ns, dtype=np.int32)
+    out = out or {}
+    gamma = out.get("gamma") if out.get("gamma") is not None else np.empty((ns, na, nt))
+    val = out.get("val") if out.get("val") is not None else np.empty(ns)
+    sig = out.get("sigma0") if out.get("sigma0") is not None else np.empty(ns)
+    idx = out.get("idx") if out.get("idx") is not None else np.empty(ns, dtype=np.int32)
+    xbest = None
+    if want_xbest:
+        xbest = out.get("xbest") if out.get("xbest") is not None else np.empty((ns, nl))
     import ctypes
     nbad = ctypes.c_int(0)
     p = lambda a: a.ctypes.data
     rc = lib.ibs_scan_host(p(tab_mn), p(tab_nyq), p(scal), p(xm), p(xn), p(xmq), p(xnq), ns, len(xm), len(xmq),
                            float(st.phiedge), float(st.Aminor_p), p(alpha), na, p(theta0), nt, p(theta), nl,
-                           grid_spacing(theta), p(gamma), p(val), p(idx), p(sig), ctypes.addressof(nbad))
+                           grid_spacing(theta), p(gamma), p(val), p(idx), p(sig),
+                           None if xbest is None else p(xbest), ctypes.addressof(nbad))
     _lib.check(rc, "ibs_scan_host")
+    if want_xbest:
+        return gamma, val, idx, sig, nbad.value, xbest
     return gamma, val, idx, sig, nbad.value

@@ -153,13 +153,15 @@ int ibs_count_above_batch(const double* g, const double* c, const double* f, int
 /* ---- end-to-end host entry point -----------------------------------------------------------------
  * Coarse scan of ball_scan.py:248-295 for ns surfaces with HOST buffers: copies the tables to the
  * device, runs K1 (ns x nalpha lines), K3 (ns x nalpha x nth0 solves) and the arg-max, and copies
- * gamma [ns][nalpha][nth0] and the per-surface (val, idx, sigma0) back.  Synchronous.              */
+ * gamma [ns][nalpha][nth0], the per-surface (val, idx, sigma0) and (if xbest_out != NULL) the
+ * eigenfunction X [ns][nl] of each surface's arg-max solve back.  Synchronous.                     */
 int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* scal,
                   const double* xm, const double* xn, const double* xm_nyq, const double* xn_nyq,
                   int ns, int mnmax, int mnmax_nyq, double phiedge, double aminor_p,
                   const double* alpha, int nalpha, const double* theta0, int nth0,
                   const double* theta, int nl, double h,
-                  double* gamma_out, double* val_out, int* idx_out, double* sigma0_out, int* nbad_out);
+                  double* gamma_out, double* val_out, int* idx_out, double* sigma0_out, double* xbest_out,
+                  int* nbad_out);
 
 #ifdef __cplusplus
 }
