@@ -1,0 +1,106 @@
+"""CPU: host-side logic -- radial splines -> per-surface tables (the geometry kernel's input contract),
+synthetic equilibria, grid helpers, sharding arithmetic."""
+import numpy as np
+import pytest
+
+from helpers import tables_from_fixture
+
+
+def test_radial_splines_match_reference_fitpack(golden):
+    """RadialSplines.evaluate (vectorised not-a-knot cubic) vs the tables the REFERENCE's FITPACK splines
+    produced (utils.py:37-158, 311-357), stored in the fixtures."""
+    from ideal_ballooning_solver_b200 import synthetic, tables
+    for name, kind in (("synthetic_ncsx", "ncsx"), ("synthetic_d3d", "d3d"), ("synthetic_hberg", "hberg")):
+        D = golden(name)
+        st = tables.RadialSplines(synthetic.make_equilibrium(kind)).evaluate(D["surfaces"])
+        for got, key in ((st.tab_mn, "tab_mn"), (st.tab_nyq, "tab_nyq"), (st.scal, "scal")):
+            ref = D[key]
+            assert got.shape == ref.shape
+            assert np.max(np.abs(got - ref)) <= 1e-11 * max(1.0, np.max(np.abs(ref))), (name, key)
+        assert np.array_equal(st.xm, D["xm"]) and np.array_equal(st.xn_nyq, D["xn_nyq"])
+
+
+def test_synthetic_equilibria_have_the_device_mode_counts():
+    from ideal_ballooning_solver_b200 import synthetic
+    for kind, mn, mnq, nfp in (("d3d", 80, 84, 1), ("ncsx", 242, 392, 3), ("hberg", 242, 392, 2)):
+        w = synthetic.make_equilibrium(kind, seed=1)
+        assert w.rmnc.shape[0] == mn and w.bmnc.shape[0] == mnq and int(w.nfp) == nfp
+        assert np.all(np.mod(w.xn, nfp) == 0)
+        # deterministic in the seed
+        w2 = synthetic.make_equilibrium(kind, seed=1)
+        assert np.array_equal(w.rmnc, w2.rmnc)
+
+
+def test_s_alpha_coefficients_formula():
+    """bishop_ball_s-alpha.py:30-45."""
+    from ideal_ballooning_solver_b200 import synthetic
+    th = np.linspace(-3, 3, 11)
+    g, c, f = synthetic.s_alpha_coefficients(0.7, 0.5, 0.2, th)
+    lam = 0.7 * (th - 0.2) - 0.5 * (np.sin(th) - np.sin(0.2))
+    np.testing.assert_allclose(g, 1 + lam ** 2)
+    np.testing.assert_allclose(c, 0.5 * (np.cos(th) + lam * np.sin(th)))
+    np.testing.assert_allclose(f, g)
+
+
+def test_grid_spacing_is_the_reference_h():
+    """utils.py:1567-1575: h = np.diff(theta_half)[2]."""
+    from ideal_ballooning_solver_b200 import engine
+    from oracle import ballooning_oracle as bo
+    th = np.linspace(-4 * np.pi, 4 * np.pi, 969)
+    one = np.ones_like(th)
+    assert engine.grid_spacing(th) == bo.discretise(th, one, one, one)[0]
+
+
+def test_shard_range_partitions():
+    from ideal_ballooning_solver_b200 import scan
+    for n in (0, 1, 5, 64, 129):
+        for world in (1, 2, 3, 8):
+            parts = [scan.shard_range(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_scan_theta_grid_matches_reference_resolution():
+    from ideal_ballooning_solver_b200 import scan
+    assert len(scan.scan_theta_grid(80, 0)) == 641            # D3D: 2*80*4+1   (ball_scan.py:206-208)
+    assert len(scan.scan_theta_grid(11, 11)) == 969           # NCSX: 2*11*11*4+1 (ball_scan.py:201-204)
+
+
+def test_surface_tables_select_and_rows(golden):
+    D = golden("ncsx_wout_op")
+    st = tables_from_fixture(D)
+    sub = st.select([2, 0])
+    assert sub.ns == 2 and np.array_equal(sub.s, D["scal"][[2, 0], 0])
+    assert sub.row("lmns").shape == (2, 242) and sub.row("bsubvmnc").shape == (2, 392)
+    np.testing.assert_allclose(sub.row("shat"), (-2 * sub.row("s") / sub.row("iota")) * sub.row("d_iota_d_s"))
+
+
+def test_read_wout_roundtrip(tmp_path):
+    """NetCDF-3 reader used for real VMEC files."""
+    from scipy.io import netcdf_file
+    from ideal_ballooning_solver_b200 import synthetic, tables
+    w = synthetic.make_equilibrium("d3d", seed=2)
+    p = str(tmp_path / "wout_test.nc")
+    with netcdf_file(p, "w") as f:
+        ns, mn, mnq = int(w.ns), w.rmnc.shape[0], w.bmnc.shape[0]
+        f.createDimension("radius", ns); f.createDimension("mn_mode", mn); f.createDimension("mn_mode_nyq", mnq)
+        f.createDimension("n_tor", len(w.raxis_cc))
+        for k in tables._TABLES_2D:
+            a = getattr(w, k)
+            v = f.createVariable(k, "d", ("radius", "mn_mode" if a.shape[0] == mn else "mn_mode_nyq"))
+            v[:] = a.T
+        for k in tables._TABLES_1D:
+            a = np.asarray(getattr(w, k), float)
+            dim = {ns: "radius", mn: "mn_mode", mnq: "mn_mode_nyq"}.get(len(a), "n_tor")
+            if mn == mnq and k.endswith("_nyq"):
+                dim = "mn_mode_nyq"
+            v = f.createVariable(k, "d", (dim,)); v[:] = a
+        for k in tables._SCALARS:
+            val = getattr(w, k)
+            v = f.createVariable(k, "d" if isinstance(val, float) else "i", ()); v[...] = val
+    r = tables.read_wout(p)
+    assert np.array_equal(r.rmnc, w.rmnc) and np.array_equal(r.bsubvmnc, w.bsubvmnc) and r.nfp == w.nfp
+    a = tables.RadialSplines(r).evaluate([0.5, 0.9]); b = tables.RadialSplines(w).evaluate([0.5, 0.9])
+    assert np.array_equal(a.tab_mn, b.tab_mn) and np.array_equal(a.scal, b.scal)
