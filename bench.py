@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="d3d", choices=sorted(WORKLOADS))
     ap.add_argument("--equilibria", type=int, default=16, help="independent equilibria batched per step per GPU")
+    ap.add_argument("--chain", type=int, default=-1, help="warm-start run length over theta0 (-1 = scan default, 1 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -231,6 +232,7 @@ def main():
     _lib.load(build_if_missing=True)
 
     E = args.equilibria
+    chain = scan.chain_length(WORKLOADS[args.workload][3]) if args.chain < 0 else max(1, args.chain)
     st, alpha, theta0, theta = build_tables(args.workload, E, seed0=1000 * rank)
     kind, ns1, na, nt, nth, span = WORKLOADS[args.workload]
     N = nth + 1
@@ -251,7 +253,7 @@ def main():
         if timers is not None:
             timers[1].record()
         sol = engine.solve_base_batch(geo.base, geo.dPdrho, th0_d, h, nth0=nt, want_X=True, want_dX=False,
-                                      want_matrix=False)
+                                      want_matrix=False, chain_len=chain)
         if timers is not None:
             timers[2].record()
         val, idx, sig = engine.scan_argmax(sol.lam.reshape(ns, na * nt))
@@ -340,6 +342,7 @@ def main():
         "config": {"workload": describe(args.workload, E), "solves_per_step_per_gpu": nsolve,
                    "field_lines_per_step_per_gpu": nlines, "l2": "flushed between timed steps (256 MB write)",
                    "eigvec": "X written to HBM for every solve", "mean_solver_iterations": mean_iters,
+                   "theta0_chain": chain,
                    "bad_solves": nbad},
         "roofline": {"bound": "hbm", "kernel": "solve_kernel (K2+K3)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

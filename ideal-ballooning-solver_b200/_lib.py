@@ -23,8 +23,8 @@ SIGNATURES = {
     "ibs_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "ibs_geometry_batch": (c_int, [_D, _D, _D, _D, _D, _D, _D, c_int, c_int, c_int, c_double, c_double,
                                    _D, c_int, c_int, _D, c_int, c_double, _D, _D, _D, _I, c_void_p]),
-    "ibs_solve_gcf_batch": (c_int, [_D, _D, _D, c_int, c_int, c_double, _D, _D, _D, _D, _D, _D, _I, c_void_p]),
-    "ibs_solve_base_batch": (c_int, [_D, _D, _D, _I, c_int, c_int, c_int, c_double, _D, _D,
+    "ibs_solve_gcf_batch": (c_int, [_D, _D, _D, c_int, c_int, c_double, _D, _D, c_int, _D, _D, _D, _D, _I, c_void_p]),
+    "ibs_solve_base_batch": (c_int, [_D, _D, _D, _I, c_int, c_int, c_int, c_double, _D, _D, c_int,
                                      _D, _D, _D, _D, _D, _D, _D, _I, c_void_p]),
     "ibs_adjoint_batch": (c_int, [_D, _D, _D, _D, _D, _D, _D, c_int, c_int, c_int, _D, c_void_p]),
     "ibs_adjoint_sensitivities": (c_int, [_D, _D, _D, _D, c_int, c_int, _D, _D, _D, c_void_p]),

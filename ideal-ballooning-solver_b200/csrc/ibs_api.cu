@@ -44,6 +44,14 @@ int num_sms() {
     return cached[dev];
 }
 
+// Warm-start chain used by the scan entry points: consecutive theta0 of one field line (the reference chains
+// its ARPACK start vector through the same loop, ball_scan.py:265-274).  The run length divides nth0.
+static int scan_chain_len(int nth0) {
+    int k = nth0 < 16 ? nth0 : 16;
+    while (k > 1 && nth0 % k) --k;
+    return k;
+}
+
 static SolveParams blank_params() { SolveParams p; std::memset(&p, 0, sizeof(p)); return p; }
 
 }  // namespace ibs
@@ -82,30 +90,30 @@ int ibs_geometry_batch(const double* tab_mn, const double* tab_nyq, const double
 }
 
 int ibs_solve_gcf_batch(const double* g, const double* c, const double* f, int nsolve, int N, double h,
-                        const double* lam0, const double* sigma, double* lam_out, double* lam_matrix_out,
+                        const double* lam0, const double* sigma, int chain_len, double* lam_out, double* lam_matrix_out,
                         double* X_out, double* dX_out, int* info_out, void* stream) {
-    IBS_REQUIRE(nsolve >= 0 && N >= 3, "need nsolve >= 0 and N >= 3");
+    IBS_REQUIRE(nsolve >= 0 && N >= 5, "need nsolve >= 0 and N >= 5");
     if (nsolve == 0) return IBS_OK;                 // empty batches are legal (and have null pointers)
     IBS_REQUIRE(g && c && f && lam_out, "null pointer");
     IBS_REQUIRE(h > 0.0, "h must be positive");
     SolveParams p = blank_params();
-    p.g = g; p.c = c; p.f = f; p.nsolve = nsolve; p.N = N; p.h = h; p.lam0 = lam0; p.sigma = sigma;
+    p.g = g; p.c = c; p.f = f; p.nsolve = nsolve; p.N = N; p.h = h; p.lam0 = lam0; p.sigma = sigma; p.chain_len = chain_len;
     p.lam_out = lam_out; p.lam_matrix_out = lam_matrix_out; p.X_out = X_out; p.dX_out = dX_out; p.info_out = info_out;
     return solve_dispatch(p, false, false, (cudaStream_t)stream);
 }
 
 int ibs_solve_base_batch(const double* base, const double* dPdrho, const double* theta0, const int* line_of_solve,
-                         int nth0, int nsolve, int N, double h, const double* lam0, const double* sigma,
+                         int nth0, int nsolve, int N, double h, const double* lam0, const double* sigma, int chain_len,
                          double* lam_out, double* lam_matrix_out, double* X_out, double* dX_out, double* g_out,
                          double* c_out, double* f_out, int* info_out, void* stream) {
-    IBS_REQUIRE(nsolve >= 0 && N >= 3, "need nsolve >= 0 and N >= 3");
+    IBS_REQUIRE(nsolve >= 0 && N >= 5, "need nsolve >= 0 and N >= 5");
     if (nsolve == 0) return IBS_OK;
     IBS_REQUIRE(base && dPdrho && theta0 && lam_out, "null pointer");
     IBS_REQUIRE(line_of_solve || nth0 >= 1, "need line_of_solve or nth0 >= 1");
     IBS_REQUIRE(h > 0.0, "h must be positive");
     SolveParams p = blank_params();
     p.base = base; p.dPdrho = dPdrho; p.theta0 = theta0; p.line_of_solve = line_of_solve; p.nth0 = nth0 > 0 ? nth0 : 1;
-    p.nsolve = nsolve; p.N = N; p.h = h; p.lam0 = lam0; p.sigma = sigma;
+    p.nsolve = nsolve; p.N = N; p.h = h; p.lam0 = lam0; p.sigma = sigma; p.chain_len = chain_len;
     p.lam_out = lam_out; p.lam_matrix_out = lam_matrix_out; p.X_out = X_out; p.dX_out = dX_out;
     p.g_out = g_out; p.c_out = c_out; p.f_out = f_out; p.info_out = info_out;
     return solve_dispatch(p, true, false, (cudaStream_t)stream);
@@ -141,7 +149,7 @@ int ibs_adjoint_sensitivities(const double* lam, const double* X, const double* 
 int ibs_obj_w_grad_batch(const double* base3, const double* dPdrho3, const double* theta0, int npoint, int N,
                          double h, double del_alpha, const double* lam0, double* val_out, double* grad_out,
                          double* X_out, double* dX_out, int* info_out, void* stream) {
-    IBS_REQUIRE(npoint >= 0 && N >= 3 && h > 0.0 && del_alpha != 0.0, "bad sizes");
+    IBS_REQUIRE(npoint >= 0 && N >= 5 && h > 0.0 && del_alpha != 0.0, "bad sizes");
     if (npoint == 0) return IBS_OK;
     IBS_REQUIRE(base3 && dPdrho3 && theta0 && val_out && grad_out, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
@@ -216,6 +224,7 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
         SolveParams p = blank_params();
         p.base = (double*)(d + o_base); p.dPdrho = (double*)(d + o_dp); p.theta0 = (double*)(d + o_t0); p.nth0 = nth0;
         p.nsolve = (int)nsolve; p.N = nl; p.h = h; p.lam_out = (double*)(d + o_gam); p.info_out = (int*)(d + o_info);
+        p.chain_len = scan_chain_len(nth0);
         if (xbest_out) p.X_out = (double*)(d + o_X);
         rc = solve_dispatch(p, true, false, st);
         if (rc != IBS_OK) goto done;

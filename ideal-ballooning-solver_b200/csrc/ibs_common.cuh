@@ -35,6 +35,7 @@ struct SolveParams {
     // coefficient source, mode "base"
     const double* base; const double* dPdrho; const double* theta0; const int* line_of_solve; int nth0;
     int nsolve, N; double h;
+    int chain_len;      // > 1: runs of chain_len consecutive solves share a CTA and warm-start each other
     const double* lam0; const double* sigma;
     double* lam_out; double* lam_matrix_out; double* X_out; double* dX_out;
     double* g_out; double* c_out; double* f_out; int* info_out;

@@ -141,7 +141,7 @@ def _alloc_out(n, N, dev, want_X, want_dX, want_matrix):
 
 
 def solve_gcf_batch(g, c, f, h: float, lam0=None, sigma=None, want_X=True, want_dX=True,
-                    want_matrix=True) -> Solution:
+                    want_matrix=True, chain_len: int = 1) -> Solution:
     """K2+K3: batched ``gamma_ball_full`` from explicit ``g, c, f`` of shape ``(nsolve, N)``
     (``utils.py:1550-1624``)."""
     _lib.require_cuda()
@@ -157,18 +157,20 @@ def solve_gcf_batch(g, c, f, h: float, lam0=None, sigma=None, want_X=True, want_
     sigma = None if sigma is None else _f64(sigma, dev, "sigma")
     lam, lm, X, dX, info = _alloc_out(n, N, dev, want_X, want_dX, want_matrix)
     with torch.cuda.device(dev):
-        rc = lib.ibs_solve_gcf_batch(_ptr(g), _ptr(c), _ptr(f), n, N, float(h), _ptr(lam0), _ptr(sigma),
+        rc = lib.ibs_solve_gcf_batch(_ptr(g), _ptr(c), _ptr(f), n, N, float(h), _ptr(lam0), _ptr(sigma), int(chain_len),
                                      _ptr(lam), _ptr(lm), _ptr(X), _ptr(dX), _ptr(info), _stream())
     _lib.check(rc, "ibs_solve_gcf_batch")
     return Solution(lam, lm, X, dX, info)
 
 
 def solve_base_batch(base, dPdrho, theta0, h: float, nth0: Optional[int] = None, line_of_solve=None, lam0=None,
-                     sigma=None, want_X=True, want_dX=True, want_matrix=True, want_gcf=False) -> Solution:
+                     sigma=None, want_X=True, want_dX=True, want_matrix=True, want_gcf=False,
+                     chain_len: int = 1) -> Solution:
     """K2+K3 with the coefficients formed on the fly from the eight base arrays of each field line
     (``ball_scan.py:267-268`` + ``utils.py:1560-1562``).  ``base`` is ``(nline, 8, N)`` (leading dims
     are flattened), ``theta0`` is ``(nsolve,)``; solve ``i`` uses line ``line_of_solve[i]`` or
-    ``i // nth0``."""
+    ``i // nth0``.  ``chain_len > 1`` warm-starts runs of consecutive solves of one line from each other
+    (the batched form of the reference's start-vector chain, ``ball_scan.py:265-274``)."""
     _lib.require_cuda()
     lib = _lib.load()
     dev = base.device
@@ -193,8 +195,8 @@ def solve_base_batch(base, dPdrho, theta0, h: float, nth0: Optional[int] = None,
     go = [torch.empty((n, N), dtype=torch.float64, device=dev) for _ in range(3)] if want_gcf else [None] * 3
     with torch.cuda.device(dev):
         rc = lib.ibs_solve_base_batch(_ptr(base), _ptr(dP), _ptr(theta0), _ptr(line_of_solve), int(nth0 or 1), n, N,
-                                      float(h), _ptr(lam0), _ptr(sigma), _ptr(lam), _ptr(lm), _ptr(X), _ptr(dX),
-                                      _ptr(go[0]), _ptr(go[1]), _ptr(go[2]), _ptr(info), _stream())
+                                      float(h), _ptr(lam0), _ptr(sigma), int(chain_len), _ptr(lam), _ptr(lm), _ptr(X),
+                                      _ptr(dX), _ptr(go[0]), _ptr(go[1]), _ptr(go[2]), _ptr(info), _stream())
     _lib.check(rc, "ibs_solve_base_batch")
     return Solution(lam, lm, X, dX, info, *go)
 

@@ -31,6 +31,15 @@ def scan_theta_grid(mpol: int, ntor: int, theta_fac: int = THETA_FAC) -> np.ndar
     return np.linspace(-theta_fac * np.pi, theta_fac * np.pi, ntheta)
 
 
+def chain_length(nth0: int, cap: int = 16) -> int:
+    """Warm-start run length over consecutive theta0 of one field line (``ball_scan.py:265-274`` chains its
+    start vector through the same loop): the largest divisor of ``nth0`` not above ``cap``."""
+    k = min(int(nth0), cap)
+    while k > 1 and nth0 % k:
+        k -= 1
+    return max(k, 1)
+
+
 def shard_range(n: int, rank: int, world: int):
     """Contiguous block of ``range(n)`` owned by ``rank`` (sizes differ by at most one)."""
     base, rem = divmod(n, world)
@@ -63,7 +72,7 @@ def coarse_scan(tables: engine.DeviceTables, alpha, theta0, theta, want_X: bool 
     ns, na, nt = tables.ns, alpha_t.shape[-1], theta0_t.numel()
     th0 = theta0_t.repeat(ns * na)
     sol = engine.solve_base_batch(geo.base, geo.dPdrho, th0, engine.grid_spacing(theta_np), nth0=nt, lam0=lam0,
-                                  want_X=want_X, want_dX=False, want_matrix=False)
+                                  want_X=want_X, want_dX=False, want_matrix=False, chain_len=chain_length(nt))
     gamma = sol.lam.reshape(ns, na, nt)
     val, idx, sig = engine.scan_argmax(gamma)
     safe = idx.clamp(min=0).long()

@@ -87,11 +87,15 @@ int ibs_geometry_batch(const double* tab_mn, const double* tab_nyq, const double
  *   lam0   [nsolve] or NULL: optional starting shifts (any value is safe)
  *   sigma  [nsolve] or NULL: if given, IBS_FLAG_SIGMA_NOT_MAX is raised when ARPACK's
  *          "eigenvalue nearest sigma" (utils.py:1597) would not be lambda_max
+ *   chain_len: > 1 = runs of chain_len consecutive solves are processed back to back by one CTA and each
+ *          is warm-started from its predecessor's eigenvalue -- the batched form of the start-vector chain
+ *          of ball_scan.py:265-274 (in the base-array entry point a chain never crosses field lines);
+ *          <= 1 = independent solves.  Either way every solve is converged to the same tolerance.
  *   lam_out [nsolve]: the reference's returned `gam`; lam_matrix_out [nsolve] or NULL: lambda_max of
  *          the pencil itself; X_out, dX_out [nsolve][N] or NULL (X >= 0, max X = 1);
  *   info_out [nsolve] or NULL.                                                                        */
 int ibs_solve_gcf_batch(const double* g, const double* c, const double* f, int nsolve, int N, double h,
-                        const double* lam0, const double* sigma,
+                        const double* lam0, const double* sigma, int chain_len,
                         double* lam_out, double* lam_matrix_out, double* X_out, double* dX_out,
                         int* info_out, void* stream);
 
@@ -105,7 +109,7 @@ int ibs_solve_gcf_batch(const double* g, const double* c, const double* f, int n
  *   g_out, c_out, f_out [nsolve][N] or NULL: the coefficient arrays gamma_ball_full returns.      */
 int ibs_solve_base_batch(const double* base, const double* dPdrho, const double* theta0,
                          const int* line_of_solve, int nth0, int nsolve, int N, double h,
-                         const double* lam0, const double* sigma,
+                         const double* lam0, const double* sigma, int chain_len,
                          double* lam_out, double* lam_matrix_out, double* X_out, double* dX_out,
                          double* g_out, double* c_out, double* f_out, int* info_out, void* stream);
 

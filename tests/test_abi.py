@@ -61,11 +61,11 @@ def test_built_for_sm_100a(lib):
 def test_version_and_argument_errors_without_gpu(lib):
     assert lib.ibs_version() >= 100
     # argument validation happens before any CUDA call and reports through ibs_last_error()
-    rc = lib.ibs_solve_gcf_batch(None, None, None, 4, 2, 0.1, None, None, None, None, None, None, None, None)
-    assert rc == 1 and b"N >= 3" in lib.ibs_last_error()
-    rc = lib.ibs_solve_gcf_batch(None, None, None, 4, 65, 0.1, None, None, None, None, None, None, None, None)
+    rc = lib.ibs_solve_gcf_batch(None, None, None, 4, 2, 0.1, None, None, 1, None, None, None, None, None, None)
+    assert rc == 1 and b"N >= 5" in lib.ibs_last_error()
+    rc = lib.ibs_solve_gcf_batch(None, None, None, 4, 65, 0.1, None, None, 1, None, None, None, None, None, None)
     assert rc == 1 and b"null" in lib.ibs_last_error()
-    assert lib.ibs_solve_gcf_batch(None, None, None, 0, 65, 0.1, None, None, None, None, None, None, None, None) == 0
+    assert lib.ibs_solve_gcf_batch(None, None, None, 0, 65, 0.1, None, None, 1, None, None, None, None, None, None) == 0
 
 
 def test_no_cpu_fallback():

@@ -101,7 +101,8 @@ def test_coarse_scan_and_argmax(cuda_lib, golden, name):
     np.testing.assert_allclose(sig.item(), s0, rtol=1e-9)
     g2, v2, i2, s2, nbad = eng.scan_host(st, a_scan, t_scan, D["theta"])
     assert nbad == 0 and i2[0] == idx.item()
-    np.testing.assert_array_equal(g2[0], gam.cpu().numpy()[0])
+    # ibs_scan_host chains the warm start over theta0; both are converged to the same tolerance
+    np.testing.assert_allclose(g2[0], gam.cpu().numpy()[0], rtol=1e-12, atol=0)
 
 
 def test_argmax_guards_bit_exact(cuda_lib):
