@@ -11,7 +11,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libibs_b200.so")
+LIB_PATH = os.environ.get("IBS_LIB") or os.path.join(HERE, "lib", "libibs_b200.so")      # IBS_LIB: tuning builds
 
 _D = c_void_p      # device/host double*
 _I = c_void_p      # int*
