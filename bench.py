@@ -40,7 +40,7 @@ WORKLOADS = {
     "ncsx":  ("ncsx",  64,  32,    32,  2048,  4),
     "hberg": ("hberg", 256, 64,    1,   8192,  8),
 }
-KERNELS_PER_STEP = 6        # pack_mn, pack_nyq, geometry, dpdrho, solve, argmax
+KERNELS_PER_STEP = 7        # pack_mn, pack_nyq, geometry, dpdrho, poly_prep, solve, argmax  (profiles/launches_*.csv)
 
 
 def workload_grids(name):
@@ -348,7 +348,7 @@ def main():
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": solve_ms,
                      "share_of_step": float(t_solve.sum() / t_step.sum()),
-                     "note": "fp64-issue bound, not HBM bound (see DESIGN.md): frac is the HBM fraction asked for"},
+                     "note": "FP64-pipe / latency bound, not HBM bound (DESIGN.md section 3): frac is the HBM fraction asked for; traffic = ncu dram bytes per launch"},
         "kernel_ms": {"geometry(K1 incl. pack+dPdrho)": float(t_geo.mean()), "solve(K2+K3)": solve_ms,
                       "step": float(t_step.mean())},
         "gpu_launches": KERNELS_PER_STEP * args.steps,

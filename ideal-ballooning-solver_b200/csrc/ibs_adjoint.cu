@@ -207,6 +207,24 @@ int launch_gather_best(const double* X, const int* idx, int ns, int ngrid, int N
     return IBS_OK;
 }
 
+// (line, theta0) of each surface's arg-max solve (flat index 0 when the all-zero guard fired)
+__global__ void best_setup_kernel(const int* __restrict__ idx, const double* __restrict__ theta0, int ns, int ngrid, int nth0,
+                                  int* __restrict__ line_out, double* __restrict__ th0_out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    const int k = idx[s] < 0 ? 0 : idx[s];
+    const int flat = s * ngrid + k;
+    line_out[s] = flat / nth0;
+    th0_out[s] = theta0[flat];
+}
+int launch_best_setup(const int* idx, const double* theta0, int ns, int ngrid, int nth0, int* line_out, double* th0_out,
+                      cudaStream_t st) {
+    if (ns == 0) return IBS_OK;
+    best_setup_kernel<<<(ns + 127) / 128, 128, 0, st>>>(idx, theta0, ns, ngrid, nth0, line_out, th0_out);
+    IBS_CUDA_CHECK(cudaGetLastError());
+    return IBS_OK;
+}
+
 int launch_adjoint(const double* lam, const double* X, const double* dX, const double* f, const double* g_p,
                    const double* c_p, const double* f_p, int nsolve, int nparam, int N, double* grad,
                    cudaStream_t st) {

@@ -25,6 +25,8 @@ int launch_obj_grad(const double* base3, const double* dPdrho3, const double* th
 int launch_centre_lines(int* line, int n, cudaStream_t st);
 int launch_argmax(const double* gamma, int ns, int ngrid, double* val, int* idx, double* sigma0, cudaStream_t st);
 int launch_gather_best(const double* X, const int* idx, int ns, int ngrid, int N, double* out, cudaStream_t st);
+int launch_best_setup(const int* idx, const double* theta0, int ns, int ngrid, int nth0, int* line_out, double* th0_out,
+                      cudaStream_t st);
 
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
@@ -191,6 +193,13 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
                   double* gamma_out, double* val_out, int* idx_out, double* sigma0_out, double* xbest_out, int* nbad_out) {
     IBS_REQUIRE(tab_mn && tab_nyq && scal && alpha && theta0 && theta && gamma_out, "null pointer");
     IBS_REQUIRE(ns >= 1 && nalpha >= 1 && nth0 >= 1 && nl >= 3, "bad sizes");
+    {   // keep stream-ordered allocations cached in the device pool between calls (default: released at every sync)
+        int dev = 0; cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     cudaStream_t st = nullptr;
     IBS_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     const size_t nlines = (size_t)ns * nalpha, nsolve = nlines * nth0;
@@ -202,7 +211,8 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
                  o_th = take((size_t)nl * 8), o_t0 = take(nsolve * 8), o_base = take(nlines * IBS_NBASE * nl * 8),
                  o_dp = take(nlines * 8), o_gam = take(nsolve * 8), o_val = take((size_t)ns * 8), o_sig = take((size_t)ns * 8),
                  o_idx = take((size_t)ns * 4), o_info = take(nsolve * 4),
-                 o_X = take(xbest_out ? nsolve * nl * 8 : 0), o_xb = take(xbest_out ? (size_t)ns * nl * 8 : 0);
+                 o_xb = take(xbest_out ? (size_t)ns * nl * 8 : 0), o_bl = take((size_t)ns * 4), o_bt = take((size_t)ns * 8),
+                 o_bg = take((size_t)ns * 8);
     char* d = nullptr;
     int rc = IBS_OK;
     std::vector<double> t0_rep(nsolve);
@@ -225,14 +235,21 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
         p.base = (double*)(d + o_base); p.dPdrho = (double*)(d + o_dp); p.theta0 = (double*)(d + o_t0); p.nth0 = nth0;
         p.nsolve = (int)nsolve; p.N = nl; p.h = h; p.lam_out = (double*)(d + o_gam); p.info_out = (int*)(d + o_info);
         p.chain_len = scan_chain_len(nth0);
-        if (xbest_out) p.X_out = (double*)(d + o_X);
         rc = solve_dispatch(p, true, false, st);
         if (rc != IBS_OK) goto done;
     }
     rc = launch_argmax((double*)(d + o_gam), ns, nalpha * nth0, (double*)(d + o_val), (int*)(d + o_idx), (double*)(d + o_sig), st);
     if (rc != IBS_OK) goto done;
     if (xbest_out) {
-        rc = launch_gather_best((double*)(d + o_X), (int*)(d + o_idx), ns, nalpha * nth0, nl, (double*)(d + o_xb), st);
+        // eigenfunction of each surface's arg-max only: re-solve those ns problems with the eigenvector written out
+        // (instead of writing nsolve eigenvectors and gathering ns of them)
+        rc = launch_best_setup((int*)(d + o_idx), (double*)(d + o_t0), ns, nalpha * nth0, nth0, (int*)(d + o_bl), (double*)(d + o_bt), st);
+        if (rc != IBS_OK) goto done;
+        SolveParams pb = blank_params();
+        pb.base = (double*)(d + o_base); pb.dPdrho = (double*)(d + o_dp); pb.theta0 = (double*)(d + o_bt);
+        pb.line_of_solve = (int*)(d + o_bl); pb.nth0 = 1; pb.nsolve = ns; pb.N = nl; pb.h = h;
+        pb.lam_out = (double*)(d + o_bg); pb.X_out = (double*)(d + o_xb);
+        rc = solve_dispatch(pb, true, false, st);
         if (rc != IBS_OK) goto done;
         IBS_TRY(cudaMemcpyAsync(xbest_out, d + o_xb, (size_t)ns * nl * 8, cudaMemcpyDeviceToHost, st));
     }
