@@ -352,6 +352,7 @@ def main():
         "kernel_ms": {"geometry(K1 incl. pack+dPdrho)": float(t_geo.mean()), "solve(K2+K3)": solve_ms,
                       "step": float(t_step.mean())},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "step_ms": {"min": float(t_step.min()), "median": float(np.median(t_step)), "max": float(t_step.max())},
         "clocks": clocks, "wall_s_timed_region": wall,
     }
     if e2e:

@@ -54,6 +54,18 @@ static int scan_chain_len(int nth0) {
     return k;
 }
 
+void keep_pool_cached() {
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[dev] = true;
+}
+
 static SolveParams blank_params() { SolveParams p; std::memset(&p, 0, sizeof(p)); return p; }
 
 }  // namespace ibs
@@ -112,6 +124,7 @@ int ibs_solve_base_batch(const double* base, const double* dPdrho, const double*
     if (nsolve == 0) return IBS_OK;
     IBS_REQUIRE(base && dPdrho && theta0 && lam_out, "null pointer");
     IBS_REQUIRE(line_of_solve || nth0 >= 1, "need line_of_solve or nth0 >= 1");
+    keep_pool_cached();
     IBS_REQUIRE(h > 0.0, "h must be positive");
     SolveParams p = blank_params();
     p.base = base; p.dPdrho = dPdrho; p.theta0 = theta0; p.line_of_solve = line_of_solve; p.nth0 = nth0 > 0 ? nth0 : 1;
@@ -193,13 +206,7 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
                   double* gamma_out, double* val_out, int* idx_out, double* sigma0_out, double* xbest_out, int* nbad_out) {
     IBS_REQUIRE(tab_mn && tab_nyq && scal && alpha && theta0 && theta && gamma_out, "null pointer");
     IBS_REQUIRE(ns >= 1 && nalpha >= 1 && nth0 >= 1 && nl >= 3, "bad sizes");
-    {   // keep stream-ordered allocations cached in the device pool between calls (default: released at every sync)
-        int dev = 0; cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long thr = ~0ULL;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-    }
+    keep_pool_cached();
     cudaStream_t st = nullptr;
     IBS_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     const size_t nlines = (size_t)ns * nalpha, nsolve = nlines * nth0;

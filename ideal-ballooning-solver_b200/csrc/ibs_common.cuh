@@ -27,6 +27,9 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 int num_sms();
+// Keep stream-ordered allocations cached in the device's default memory pool between calls (by default the pool
+// hands everything back to the driver at the next synchronisation, so every call would pay cudaMalloc again).
+void keep_pool_cached();
 
 // Argument block of the solver kernels (K2+K3), shared by ibs_solver.cu and ibs_api.cu.
 struct SolveParams {

@@ -421,6 +421,7 @@ int geometry_dispatch(const double* tab_mn, const double* tab_nyq, const double*
         }
         d_idx = cached_dev;
     }
+    keep_pool_cached();
     IBS_CUDA_CHECK(cudaMallocAsync((void**)&pk, (n_mn + n_nyq) * sizeof(double), st));
     IBS_CUDA_CHECK(cudaMemsetAsync(pk, 0, (n_mn + n_nyq) * sizeof(double), st));
     pack_mn_kernel<<<dim3((mnmax + 127) / 128, ns), 128, 0, st>>>(tab_mn, d_idx, d_idx + mnmax, ns, mnmax, M1, W1, NT1, nfp, pk);
