@@ -232,7 +232,9 @@ def main():
     _lib.load(build_if_missing=True)
 
     E = args.equilibria
-    chain = scan.chain_length(WORKLOADS[args.workload][3]) if args.chain < 0 else max(1, args.chain)
+    _, _, na_w, nt_w, _, _ = WORKLOADS[args.workload]
+    # warm-start chain over theta0 (or over alpha when the scan has a single theta0), ball_scan.py:265-274
+    chain = scan.chain_length(nt_w if nt_w > 1 else na_w) if args.chain < 0 else max(1, args.chain)
     st, alpha, theta0, theta = build_tables(args.workload, E, seed0=1000 * rank)
     kind, ns1, na, nt, nth, span = WORKLOADS[args.workload]
     N = nth + 1

@@ -89,7 +89,8 @@ int ibs_geometry_batch(const double* tab_mn, const double* tab_nyq, const double
  *          "eigenvalue nearest sigma" (utils.py:1597) would not be lambda_max
  *   chain_len: > 1 = runs of chain_len consecutive solves are processed back to back by one CTA and each
  *          is warm-started from its predecessor's eigenvalue -- the batched form of the start-vector chain
- *          of ball_scan.py:265-274 (in the base-array entry point a chain never crosses field lines);
+ *          of ball_scan.py:265-274 (in the base-array entry point a chain never crosses field lines, except when
+ *          nth0 == 1, i.e. an alpha scan with one solve per line, where consecutive lines are chained);
  *          <= 1 = independent solves.  Either way every solve is converged to the same tolerance.
  *   lam_out [nsolve]: the reference's returned `gam`; lam_matrix_out [nsolve] or NULL: lambda_max of
  *          the pencil itself; X_out, dX_out [nsolve][N] or NULL (X >= 0, max X = 1);
