@@ -225,6 +225,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line (NCCL prints its version banner)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank if world > 1 else torch.cuda.current_device())
@@ -321,6 +322,9 @@ def main():
         e2e = {"value": world * nsolve * ke / dt_e.item(), "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "bad_solves": int(r[4])}
 
+    if world > 1 and os.environ.get("IBS_BENCH_VERBOSE"):
+        print(f"[rank {rank}] step ms min/med/max {t_step.min():.3f}/{np.median(t_step):.3f}/{t_step.max():.3f} geo {t_geo.mean():.3f} "
+              f"solve {t_solve.mean():.3f} iters {mean_iters:.2f}", file=sys.stderr, flush=True)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

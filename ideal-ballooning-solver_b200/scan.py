@@ -126,3 +126,172 @@ def sharded_coarse_scan(st: SurfaceTables, alpha, theta0, theta, device=None, wa
     res = coarse_scan(dt, alpha, theta0, theta, want_X=want_X)
     val_all, idx_all = gather_surface_maxima(res.val, res.idx, st.ns, group)
     return res, (lo, hi), val_all, idx_all
+
+
+# ---------------------------------------------------------------------------------------------
+# Refinement of the coarse maxima and the drop-in driver
+# ---------------------------------------------------------------------------------------------
+class _BatchedObjective:
+    """Lets ``ns`` independent ``scipy.optimize.minimize`` instances (one Python thread per surface, exactly the
+    reference's optimiser and options, ``ball_scan.py:305-314``) share ONE batched GPU evaluation of
+    ``obj_w_grad`` per round: every thread posts its ``(alpha, theta0)`` and blocks; the thread that completes
+    the round runs K1 (three field lines per point) + K3 + K4 for all pending points and wakes the others."""
+
+    def __init__(self, tables: engine.DeviceTables, theta_np, del_alpha=DEL_ALPHA):
+        import threading
+        self.tables, self.theta = tables, theta_np
+        self.h = engine.grid_spacing(theta_np)
+        self.del_alpha = del_alpha
+        self.cv = threading.Condition()
+        self.active = set()
+        self.pending = {}
+        self.results = {}
+        self.nbatches = 0
+        self.nevals = 0
+
+    def start(self, ids):
+        self.active = set(ids)
+
+    def _run_batch(self):
+        ids = sorted(self.pending)
+        xs = np.array([self.pending[i] for i in ids], dtype=np.float64)
+        dev = self.tables.tab_mn.device
+        sel = torch.as_tensor(ids, device=dev, dtype=torch.long)
+        sub = dataclasses.replace(self.tables, tab_mn=self.tables.tab_mn.index_select(0, sel).contiguous(),
+                                  tab_nyq=self.tables.tab_nyq.index_select(0, sel).contiguous(),
+                                  scal=self.tables.scal.index_select(0, sel).contiguous())
+        d = self.del_alpha
+        alphas = np.stack([xs[:, 0] - 0.5 * d, xs[:, 0], xs[:, 0] + 0.5 * d], axis=1)        # utils.py:1641-1646
+        geo = engine.geometry_batch(sub, torch.from_numpy(alphas).to(dev), self.theta)
+        val, grad, _, _, info = engine.obj_w_grad_batch(geo.base, geo.dPdrho, torch.from_numpy(xs[:, 1].copy()).to(dev),
+                                                        self.h, del_alpha=d)
+        val, grad, info = val.cpu().numpy(), grad.cpu().numpy(), info.cpu().numpy()
+        for k, i in enumerate(ids):
+            self.results[i] = (float(val[k]), grad[k].copy(), int(info[k]) >> 16)
+        self.pending.clear()
+        self.nbatches += 1
+        self.nevals += len(ids)
+
+    def evaluate(self, i, x):
+        with self.cv:
+            self.pending[i] = (float(x[0]), float(x[1]))
+            if len(self.pending) == len(self.active):
+                self._run_batch()
+                self.cv.notify_all()
+            else:
+                while i not in self.results:
+                    self.cv.wait()
+            val, grad, flags = self.results.pop(i)
+        if flags & (engine.FLAG_NOT_CONVERGED | engine.FLAG_BAD_INPUT):
+            raise RuntimeError("obj_w_grad: eigen-solve failed on surface %d" % i)
+        return val, grad
+
+    def finish(self, i):
+        with self.cv:
+            self.active.discard(i)
+            if self.pending and len(self.pending) == len(self.active):
+                self._run_batch()
+                self.cv.notify_all()
+
+
+@dataclasses.dataclass
+class RefineResult:
+    alpha: np.ndarray          # (ns,) alpha at the refined maximum
+    theta0: np.ndarray         # (ns,)
+    fun: np.ndarray            # (ns,) -lambda at the optimiser's last point
+    nit: np.ndarray
+    nfev: np.ndarray
+    success: np.ndarray
+    nbatches: int              # batched GPU evaluations issued (vs sum(nfev) one-at-a-time in the reference)
+
+
+def refine_maxima(tables: engine.DeviceTables, alpha_guess, theta0_guess, theta, maxiter: int = 30, ftol: float = 5.0e-11,
+                  gtol: float = 2.0e-08) -> RefineResult:
+    """``scipy.optimize.minimize(obj_w_grad, x0=(alpha_guess, theta0_guess), jac=True, bounds=((0, pi), (0, pi/2)),
+    options={ftol, gtol, maxiter})`` for every surface (``ball_scan.py:305-314``), the objective evaluated on the
+    GPU for all surfaces at once."""
+    import threading
+    from scipy.optimize import minimize
+    ns = tables.ns
+    theta_np = theta.cpu().numpy() if isinstance(theta, torch.Tensor) else np.asarray(theta, dtype=np.float64)
+    a0 = np.asarray(alpha_guess.cpu() if isinstance(alpha_guess, torch.Tensor) else alpha_guess, dtype=np.float64).reshape(ns)
+    t0 = np.asarray(theta0_guess.cpu() if isinstance(theta0_guess, torch.Tensor) else theta0_guess, dtype=np.float64).reshape(ns)
+    obj = _BatchedObjective(tables, theta_np)
+    obj.start(range(ns))
+    out = [None] * ns
+    err = [None] * ns
+
+    def worker(i):
+        try:
+            out[i] = minimize(lambda x: obj.evaluate(i, x), x0=(a0[i], t0[i]), jac=True,
+                              bounds=((0.0, np.pi), (0.0, 0.5 * np.pi)),
+                              options={"ftol": ftol, "gtol": gtol, "maxiter": maxiter})
+        except Exception as e:          # keep the other surfaces going
+            err[i] = e
+        finally:
+            obj.finish(i)
+
+    threads = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(ns)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return RefineResult(alpha=np.array([o.x[0] for o in out]), theta0=np.array([o.x[1] for o in out]),
+                        fun=np.array([float(o.fun) for o in out]), nit=np.array([o.nit for o in out]),
+                        nfev=np.array([o.nfev for o in out]), success=np.array([bool(o.success) for o in out]),
+                        nbatches=obj.nbatches)
+
+
+@dataclasses.dataclass
+class BallScanResult:
+    gamma: np.ndarray          # (ns,) maximum growth rate per surface        (ball_gam<dof>.npy row)
+    theta0: np.ndarray         # (ns,)                                         (ball_theta0<dof>.npy row)
+    alpha: np.ndarray          # (ns,)                                         (ball_alpha<dof>.npy row)
+    gamma_coarse: np.ndarray   # (ns, nalpha, ntheta0) coarse grid
+    X: np.ndarray              # (ns, nl) eigenfunction at the optimum
+    refine: Optional[RefineResult]
+
+
+def ball_scan(st: SurfaceTables, theta=None, mpol: Optional[int] = None, ntor: Optional[int] = None,
+              nalpha_guess: int = NALPHA_GUESS, ntheta0_guess: int = NTHETA0_GUESS, refine: bool = True,
+              device=None) -> BallScanResult:
+    """The numerical section of ``ball_scan.py:196-339`` for all surfaces of ``st`` at once:
+    coarse 24 x 15 (alpha, theta0) grid (``:223-274``) -> guarded arg-max (``:279-295``) -> L-BFGS-B refinement
+    from the coarse maximum with the adjoint gradient (``:305-314``) -> eigenpair at the optimum (``:322-339``)."""
+    if theta is None:
+        theta = scan_theta_grid(mpol, ntor)
+    theta = np.asarray(theta, dtype=np.float64)
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    dt = engine.DeviceTables.from_host(st, device)
+    alpha_scan = np.linspace(0, np.pi, nalpha_guess)                      # ball_scan.py:225-226
+    theta0_scan = np.linspace(0.0, 0.5 * np.pi, ntheta0_guess)
+    res = coarse_scan(dt, alpha_scan, theta0_scan, theta)
+    a_star, t_star = res.alpha_guess.cpu().numpy(), res.theta0_guess.cpu().numpy()
+    ref = None
+    if refine:
+        ref = refine_maxima(dt, a_star, t_star, theta)
+        a_star, t_star = ref.alpha, ref.theta0
+    # ball_scan.py:322-339: geometry and eigenpair at the optimum
+    geo = engine.geometry_batch(dt, torch.from_numpy(a_star[:, None].copy()).to(device), theta)
+    sol = engine.solve_base_batch(geo.base, geo.dPdrho, torch.from_numpy(t_star.copy()).to(device), engine.grid_spacing(theta),
+                                  nth0=1, want_dX=False, want_matrix=False)
+    return BallScanResult(gamma=sol.lam.cpu().numpy(), theta0=t_star, alpha=a_star, gamma_coarse=res.gamma.cpu().numpy(),
+                          X=sol.X.cpu().numpy(), refine=ref)
+
+
+def save_results(path: str, dof_idx: int, iter0: int, result: BallScanResult) -> None:
+    """Append one row per call to ``ball_gam<dof>.npy``, ``ball_theta0<dof>.npy``, ``ball_alpha<dof>.npy`` with the
+    reference's semantics (``ball_scan.py:359-384``): at ``iter0 == 0`` the placeholder first element written by
+    ``arr_create2.py`` is dropped, afterwards rows are stacked."""
+    import os
+    for name, row in (("ball_gam", result.gamma), ("ball_theta0", result.theta0), ("ball_alpha", result.alpha)):
+        fn = os.path.join(path, "%s%d.npy" % (name, int(dof_idx)))
+        old = np.load(fn, allow_pickle=True)
+        if iter0 == 0:
+            new = np.delete(np.append(old, row), 0)
+        else:
+            new = np.vstack((old, row))
+        np.save(fn, new)

@@ -1,0 +1,56 @@
+"""GPU: the drop-in scan driver (coarse grid -> guarded arg-max -> L-BFGS-B refine with the adjoint gradient ->
+eigenpair at the optimum, ball_scan.py:196-339) against the same steps done with the CPU oracle + scipy."""
+import numpy as np
+import pytest
+
+from helpers import tables_from_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_ball_scan_surface(tab, theta, alpha_scan, theta0_scan):
+    """ball_scan.py:248-339 for one surface with the oracle (LAPACK route = converged reference)."""
+    from scipy.optimize import minimize
+    from oracle import ballooning_oracle as bo
+    fl_fn = lambda alphas: bo.fieldlines(tab, alphas, theta)
+    gam = bo.coarse_scan_surface(fl_fn, theta, alpha_scan, theta0_scan, method="lambda_max")
+    ia, it, sigma0 = bo.argmax_with_guards(gam)
+    x0 = (0.0, 0.0) if ia < 0 else (alpha_scan[ia], theta0_scan[it])
+    vg = bo.default_vguess(theta)
+    obj = minimize(lambda x: bo.obj_w_grad(x, fl_fn, theta, vg, sigma0, method="lambda_max"), x0=x0, jac=True,
+                   bounds=((0.0, np.pi), (0.0, 0.5 * np.pi)), options={"ftol": 5.0e-11, "gtol": 2.0e-08, "maxiter": 30})
+    fl = fl_fn(np.array([obj.x[0]]))
+    cv, gd = bo.theta0_shift(fl, obj.x[1])
+    lam, X, *_ = bo.gamma_ball_full(bo.dpdrho_of(fl), theta, fl.bmag[0][0], fl.gradpar_theta_pest[0][0], cv, gd, method="lambda_max")
+    return gam, obj, lam
+
+
+def test_ball_scan_matches_oracle_driver(cuda_lib, golden):
+    from ideal_ballooning_solver_b200 import scan
+    D = golden("synthetic_d3d")
+    st = tables_from_fixture(D)                                   # 3 surfaces
+    theta = np.linspace(-3 * np.pi, 3 * np.pi, 193)
+    na, nt = 5, 4
+    res = scan.ball_scan(st, theta=theta, nalpha_guess=na, ntheta0_guess=nt)
+    alpha_scan, theta0_scan = np.linspace(0, np.pi, na), np.linspace(0, 0.5 * np.pi, nt)
+    assert res.refine is not None and res.refine.nbatches <= int(res.refine.nfev.max()) + 2     # evaluations were batched
+    for js in range(st.ns):
+        gam, obj, lam = _oracle_ball_scan_surface(st.select([js]), theta, alpha_scan, theta0_scan)
+        np.testing.assert_allclose(res.gamma_coarse[js], gam, rtol=1e-9, atol=1e-13)
+        # same optimiser, same options, objective equal to ~1e-10: the optimum agrees closely
+        np.testing.assert_allclose(res.gamma[js], lam, rtol=1e-6, atol=1e-10)
+        np.testing.assert_allclose([res.alpha[js], res.theta0[js]], obj.x, atol=2e-4)
+        assert res.gamma[js] >= gam.max() - 1e-12                  # the refinement never loses the coarse maximum
+        assert 0.0 <= res.alpha[js] <= np.pi and 0.0 <= res.theta0[js] <= 0.5 * np.pi
+
+
+def test_refine_batches_all_surfaces(cuda_lib, golden):
+    """64 surfaces refined together: a handful of batched GPU rounds instead of sum(nfev) launches."""
+    from ideal_ballooning_solver_b200 import engine, scan, synthetic, tables
+    st = tables.RadialSplines(synthetic.make_equilibrium("ncsx", seed=4)).evaluate(np.linspace(0.5, 0.95, 64))
+    theta = np.linspace(-4 * np.pi, 4 * np.pi, 513)
+    res = scan.ball_scan(st, theta=theta, nalpha_guess=6, ntheta0_guess=5)
+    r = res.refine
+    assert r.nbatches <= int(r.nfev.max()) + 2 and int(r.nfev.sum()) > 3 * r.nbatches
+    assert np.all(res.gamma >= res.gamma_coarse.reshape(64, -1).max(axis=1) - 1e-12)
+    assert np.all(np.isfinite(res.gamma)) and res.X.shape == (64, 513)

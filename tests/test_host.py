@@ -104,3 +104,27 @@ def test_read_wout_roundtrip(tmp_path):
     assert np.array_equal(r.rmnc, w.rmnc) and np.array_equal(r.bsubvmnc, w.bsubvmnc) and r.nfp == w.nfp
     a = tables.RadialSplines(r).evaluate([0.5, 0.9]); b = tables.RadialSplines(w).evaluate([0.5, 0.9])
     assert np.array_equal(a.tab_mn, b.tab_mn) and np.array_equal(a.scal, b.scal)
+
+
+def test_save_results_append_semantics(tmp_path):
+    """ball_scan.py:359-384 on the placeholder files of arr_create2.py:87-97."""
+    from ideal_ballooning_solver_b200 import scan
+    for nm in ("ball_gam", "ball_theta0", "ball_alpha"):
+        np.save(str(tmp_path / f"{nm}3.npy"), np.empty([]))
+    mk = lambda k: scan.BallScanResult(gamma=np.arange(5.0) + k, theta0=np.arange(5.0) * 0.1 + k, alpha=np.arange(5.0) * 0.2 + k,
+                                       gamma_coarse=np.zeros((5, 2, 2)), X=np.zeros((5, 9)), refine=None)
+    scan.save_results(str(tmp_path), 3, 0, mk(0))
+    g = np.load(str(tmp_path / "ball_gam3.npy"))
+    assert g.shape == (5,) and np.array_equal(g, np.arange(5.0))
+    scan.save_results(str(tmp_path), 3, 1, mk(10))
+    scan.save_results(str(tmp_path), 3, 2, mk(20))
+    g = np.load(str(tmp_path / "ball_gam3.npy"))
+    a = np.load(str(tmp_path / "ball_alpha3.npy"))
+    assert g.shape == (3, 5) and np.array_equal(g[2], np.arange(5.0) + 20)
+    assert np.array_equal(a[1], np.arange(5.0) * 0.2 + 10)
+
+
+def test_chain_length_divides():
+    from ideal_ballooning_solver_b200 import scan
+    assert scan.chain_length(64) == 16 and scan.chain_length(15) == 15 and scan.chain_length(24) == 12
+    assert scan.chain_length(1) == 1 and scan.chain_length(17) == 1 and scan.chain_length(32) == 16
