@@ -126,21 +126,31 @@ geometry_kernel(const GeoParams p) {
     if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
 
-    for (int js = blockIdx.y; js < p.ns; js += gridDim.y) {
-        // ---- stage this surface's packed tables in shared memory (TMA bulk copy)
-        __syncthreads();                       // everyone is done with the previous surface's tables
-        if (tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(bar, (unsigned)((n_mn + n_nyq) * sizeof(double)));
-            tma_bulk_g2s(s_mn, p.pk_mn + (size_t)js * n_mn, (unsigned)(n_mn * sizeof(double)), bar);
-            tma_bulk_g2s(s_nyq, p.pk_nyq + (size_t)js * n_nyq, (unsigned)(n_nyq * sizeof(double)), bar);
+    // Work = (surface, tile) pairs flattened; every CTA takes one contiguous, equally sized range of them (perfect
+    // balance, no tail wave) and re-stages the tables only when its range crosses into the next surface.
+    const long long W = (long long)p.ns * tiles_per_surface;
+    const long long w_begin = W * blockIdx.x / gridDim.x, w_end = W * (blockIdx.x + 1) / gridDim.x;
+    int js = -1;
+    double s_val = 0, iota = 1, d_iota = 0, dpds = 0, shat = 0;
+    for (long long w = w_begin; w < w_end; ++w) {
+        const int js_w = (int)(w / tiles_per_surface);
+        const int tile = (int)(w - (long long)js_w * tiles_per_surface);
+        if (js_w != js) {
+            js = js_w;
+            // ---- stage this surface's packed tables in shared memory (TMA bulk copy)
+            __syncthreads();                       // everyone is done with the previous surface's tables
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar, (unsigned)((n_mn + n_nyq) * sizeof(double)));
+                tma_bulk_g2s(s_mn, p.pk_mn + (size_t)js * n_mn, (unsigned)(n_mn * sizeof(double)), bar);
+                tma_bulk_g2s(s_nyq, p.pk_nyq + (size_t)js * n_nyq, (unsigned)(n_nyq * sizeof(double)), bar);
+            }
+            const double* sc = p.scal + (size_t)js * IBS_NSCAL;
+            s_val = sc[0]; iota = sc[1]; d_iota = sc[2]; dpds = sc[3]; shat = sc[4];
+            mbar_wait(bar, parity);
+            parity ^= 1;
         }
-        const double* sc = p.scal + (size_t)js * IBS_NSCAL;
-        const double s_val = sc[0], iota = sc[1], d_iota = sc[2], dpds = sc[3], shat = sc[4];
-        mbar_wait(bar, parity);
-        parity ^= 1;
-
-        for (int tile = blockIdx.x; tile < tiles_per_surface; tile += gridDim.x) {
+        {
             const int pt = tile * GEO_THREADS + tid;
             if (pt >= pts_per_surface) continue;
             const int ja = pt / p.nl, jl = pt - ja * p.nl;
@@ -357,12 +367,10 @@ static int launch_geometry(const GeoParams& p, cudaStream_t st) {
     if (per_sm < 1) per_sm = 1;
     const int tiles = (p.nalpha * p.nl + GEO_THREADS - 1) / GEO_THREADS;
     const long long slots = (long long)num_sms() * per_sm;
-    // y = surfaces (each CTA keeps one surface's tables resident), x = tiles of that surface
-    int gy = p.ns, gx = (int)((slots + gy - 1) / gy);
-    if (gx > tiles) gx = tiles;
-    if (gx < 1) gx = 1;
-    if (gy > 65535) gy = 65535;
-    kern<<<dim3(gx, gy), GEO_THREADS, smem, st>>>(p);
+    // persistent 1-D grid: one CTA per resident slot (or per tile when there is less work than that)
+    const long long W = (long long)p.ns * tiles;
+    const int grid = (int)(W < slots ? W : slots);
+    kern<<<grid, GEO_THREADS, smem, st>>>(p);
     IBS_CUDA_CHECK(cudaGetLastError());
     return IBS_OK;
 }
