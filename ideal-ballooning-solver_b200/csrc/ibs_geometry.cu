@@ -29,6 +29,11 @@ namespace ibs {
 constexpr int GEO_THREADS = 128;
 constexpr int ROW_MN = 10;    // r, n r, r_s, z, n z, z_s, l, n l, l_s, (pad)
 constexpr int ROW_NYQ = 8;    // g, b, n b, b_s, bsupv, bsubs, bsubu, bsubv
+// 3-D equilibria use a paired layout [m][|n|][row][E, O] (E = v(+n) + v(-n), O = v(+n) - v(-n)): with
+//   sum_n v_n cos(m th - n ph) = cos(m th) A + sin(m th) B,   sum_n v_n sin(m th - n ph) = sin(m th) A - cos(m th) B,
+//   A = v_0 + sum_{k>0} E_k cos(k nfp ph),  B = sum_{k>0} O_k sin(k nfp ph),
+// a mode costs one FMA per table row (no per-mode angle update): ~30 % fewer FP64 instructions than the dense +-n grid.
+constexpr int ROWP_MN = 18, ROWP_NYQ = 16;
 constexpr int MAX_M_NEWTON = 96;
 
 struct GeoParams {
@@ -51,13 +56,20 @@ __global__ void pack_mn_kernel(const double* __restrict__ tab, const int* __rest
     if (k >= mnmax) return;
     const int m = mode_m[k], nn = mode_n[k];          // nn = n / nfp
     const double* t = tab + (size_t)s * 6 * mnmax;
-    double* o = out + (((size_t)s * M1 + m) * W1 + (nn + NT1)) * ROW_MN;
     const double n = (double)(nn * nfp);
     const double r = t[0 * mnmax + k], z = t[1 * mnmax + k], l = t[2 * mnmax + k];
+    const double v[9] = {r, n * r, t[3 * mnmax + k], z, n * z, t[4 * mnmax + k], l, n * l, t[5 * mnmax + k]};
     // duplicates in the mode list are legal (they add up)
-    atomicAdd(o + 0, r); atomicAdd(o + 1, n * r); atomicAdd(o + 2, t[3 * mnmax + k]);
-    atomicAdd(o + 3, z); atomicAdd(o + 4, n * z); atomicAdd(o + 5, t[4 * mnmax + k]);
-    atomicAdd(o + 6, l); atomicAdd(o + 7, n * l); atomicAdd(o + 8, t[5 * mnmax + k]);
+    if (NT1 == 0) {
+        double* o = out + (((size_t)s * M1 + m) * W1 + (nn + NT1)) * ROW_MN;
+        for (int j = 0; j < 9; ++j) atomicAdd(o + j, v[j]);
+    } else {
+        // paired layout [m][|n|][row][E, O]:  E = v(+n) + v(-n),  O = v(+n) - v(-n)
+        const int ak = nn < 0 ? -nn : nn;
+        const double sg = nn > 0 ? 1.0 : (nn < 0 ? -1.0 : 0.0);
+        double* o = out + (((size_t)s * M1 + m) * (NT1 + 1) + ak) * ROWP_MN;
+        for (int j = 0; j < 9; ++j) { atomicAdd(o + 2 * j, v[j]); atomicAdd(o + 2 * j + 1, sg * v[j]); }
+    }
 }
 __global__ void pack_nyq_kernel(const double* __restrict__ tab, const int* __restrict__ mode_m, const int* __restrict__ mode_n,
                                 int ns, int mnmax, int M2, int W2, int NT2, int nfp, double* __restrict__ out) {
@@ -66,12 +78,18 @@ __global__ void pack_nyq_kernel(const double* __restrict__ tab, const int* __res
     if (k >= mnmax) return;
     const int m = mode_m[k], nn = mode_n[k];
     const double* t = tab + (size_t)s * 7 * mnmax;
-    double* o = out + (((size_t)s * M2 + m) * W2 + (nn + NT2)) * ROW_NYQ;
     const double n = (double)(nn * nfp);
     const double b = t[1 * mnmax + k];
-    atomicAdd(o + 0, t[0 * mnmax + k]); atomicAdd(o + 1, b); atomicAdd(o + 2, n * b); atomicAdd(o + 3, t[2 * mnmax + k]);
-    atomicAdd(o + 4, t[3 * mnmax + k]); atomicAdd(o + 5, t[4 * mnmax + k]); atomicAdd(o + 6, t[5 * mnmax + k]);
-    atomicAdd(o + 7, t[6 * mnmax + k]);
+    const double v[8] = {t[0 * mnmax + k], b, n * b, t[2 * mnmax + k], t[3 * mnmax + k], t[4 * mnmax + k], t[5 * mnmax + k], t[6 * mnmax + k]};
+    if (NT2 == 0) {
+        double* o = out + (((size_t)s * M2 + m) * W2 + (nn + NT2)) * ROW_NYQ;
+        for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
+    } else {
+        const int ak = nn < 0 ? -nn : nn;
+        const double sg = nn > 0 ? 1.0 : (nn < 0 ? -1.0 : 0.0);
+        double* o = out + (((size_t)s * M2 + m) * (NT2 + 1) + ak) * ROWP_NYQ;
+        for (int j = 0; j < 8; ++j) { atomicAdd(o + 2 * j, v[j]); atomicAdd(o + 2 * j + 1, sg * v[j]); }
+    }
 }
 
 // ---- TMA bulk copy global -> shared, completion on an mbarrier -------------------------------------------
@@ -117,7 +135,8 @@ geometry_kernel(const GeoParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     double* s_mn = reinterpret_cast<double*>(smem_raw + 16);
-    const int n_mn = p.M1 * W1 * ROW_MN, n_nyq = p.M2 * W2 * ROW_NYQ;
+    const int n_mn = (NT1 > 0) ? p.M1 * (NT1 + 1) * ROWP_MN : p.M1 * W1 * ROW_MN;
+    const int n_nyq = (NT2 > 0) ? p.M2 * (NT2 + 1) * ROWP_NYQ : p.M2 * W2 * ROW_NYQ;
     double* s_nyq = s_mn + n_mn;
     const int tid = threadIdx.x;
     const int pts_per_surface = p.nalpha * p.nl;
@@ -173,14 +192,13 @@ geometry_kernel(const GeoParams p) {
             double Am[NT1 > 0 ? MAX_M_NEWTON : 1], Bm[NT1 > 0 ? MAX_M_NEWTON : 1];
             if (NT1 > 0) {
                 for (int m = 0; m < p.M1; ++m) {
-                    const double* row = s_mn + (size_t)m * W1 * ROW_MN;
-                    double a = 0.0, b = 0.0;
+                    const double* row = s_mn + (size_t)m * (NT1 + 1) * ROWP_MN + 12;      // (E, O) of the l row
+                    double a = row[0], b = 0.0;
 #pragma unroll
-                    for (int q = 0; q < W1; ++q) {
-                        const double l = row[q * ROW_MN + 6];
-                        const int k = q - NT1;
-                        a = fma(l, cn[k < 0 ? -k : k], a);
-                        b = (k < 0) ? fma(-l, sn[-k], b) : fma(l, sn[k], b);
+                    for (int k = 1; k <= NT1; ++k) {
+                        const double2 eo = *reinterpret_cast<const double2*>(row + k * ROWP_MN);
+                        a = fma(eo.x, cn[k], a);
+                        b = fma(eo.y, sn[k], b);
                     }
                     Am[m] = a; Bm[m] = b;
                 }
@@ -210,7 +228,39 @@ geometry_kernel(const GeoParams p) {
             double s1, c1;
             sincos(th, &s1, &c1);
             double R = 0, R_s = 0, R_t = 0, R_p = 0, Z_s = 0, Z_t = 0, Z_p = 0, L_s = 0, L_t = 0, L_p = 0;
-            {
+            if (NT1 > 0) {
+                double cm = 1.0, sm = 0.0;
+                for (int m = 0; m < p.M1; ++m) {
+                    const double* row = s_mn + (size_t)m * (NT1 + 1) * ROWP_MN;
+                    double A[9], Bv[9];
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) { A[j] = row[2 * j]; Bv[j] = 0.0; }
+#pragma unroll
+                    for (int k = 1; k <= NT1; ++k) {
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) {
+                            const double2 eo = *reinterpret_cast<const double2*>(row + k * ROWP_MN + 2 * j);
+                            A[j] = fma(eo.x, cn[k], A[j]);
+                            Bv[j] = fma(eo.y, sn[k], Bv[j]);
+                        }
+                    }
+                    // rows: 0 r, 1 n r, 2 r_s, 3 z, 4 n z, 5 z_s, 6 l, 7 n l, 8 l_s
+                    const double dm = (double)m;
+                    R += fma(cm, A[0], sm * Bv[0]);
+                    R_t = fma(-dm, fma(sm, A[0], -(cm * Bv[0])), R_t);
+                    R_p += fma(sm, A[1], -(cm * Bv[1]));
+                    R_s += fma(cm, A[2], sm * Bv[2]);
+                    Z_t = fma(dm, fma(cm, A[3], sm * Bv[3]), Z_t);
+                    Z_p -= fma(cm, A[4], sm * Bv[4]);
+                    Z_s += fma(sm, A[5], -(cm * Bv[5]));
+                    L_t = fma(dm, fma(cm, A[6], sm * Bv[6]), L_t);
+                    L_p -= fma(cm, A[7], sm * Bv[7]);
+                    L_s += fma(sm, A[8], -(cm * Bv[8]));
+                    const double cnx = fma(cm, c1, -(sm * s1));
+                    sm = fma(sm, c1, cm * s1);
+                    cm = cnx;
+                }
+            } else {
                 double cm = 1.0, sm = 0.0;
                 for (int m = 0; m < p.M1; ++m) {
                     const double* row = s_mn + (size_t)m * W1 * ROW_MN;
@@ -247,7 +297,38 @@ geometry_kernel(const GeoParams p) {
                 }
             }
             double sqrtg = 0, B = 0, B_s = 0, B_t = 0, B_p = 0, Bsup_p = 0, Bsub_s = 0, Bsub_t = 0, Bsub_p = 0;
-            {
+            if (NT2 > 0) {
+                double cm = 1.0, sm = 0.0;
+                for (int m = 0; m < p.M2; ++m) {
+                    const double* row = s_nyq + (size_t)m * (NT2 + 1) * ROWP_NYQ;
+                    double A[8], Bv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { A[j] = row[2 * j]; Bv[j] = 0.0; }
+#pragma unroll
+                    for (int k = 1; k <= NT2; ++k) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const double2 eo = *reinterpret_cast<const double2*>(row + k * ROWP_NYQ + 2 * j);
+                            A[j] = fma(eo.x, cn[k], A[j]);
+                            Bv[j] = fma(eo.y, sn[k], Bv[j]);
+                        }
+                    }
+                    // rows: 0 g, 1 b, 2 n b, 3 b_s, 4 bsupv, 5 bsubs, 6 bsubu, 7 bsubv
+                    const double dm = (double)m;
+                    sqrtg += fma(cm, A[0], sm * Bv[0]);
+                    B += fma(cm, A[1], sm * Bv[1]);
+                    B_t = fma(-dm, fma(sm, A[1], -(cm * Bv[1])), B_t);
+                    B_p += fma(sm, A[2], -(cm * Bv[2]));
+                    B_s += fma(cm, A[3], sm * Bv[3]);
+                    Bsup_p += fma(cm, A[4], sm * Bv[4]);
+                    Bsub_s += fma(sm, A[5], -(cm * Bv[5]));
+                    Bsub_t += fma(cm, A[6], sm * Bv[6]);
+                    Bsub_p += fma(cm, A[7], sm * Bv[7]);
+                    const double cnx = fma(cm, c1, -(sm * s1));
+                    sm = fma(sm, c1, cm * s1);
+                    cm = cnx;
+                }
+            } else {
                 double cm = 1.0, sm = 0.0;
                 for (int m = 0; m < p.M2; ++m) {
                     const double* row = s_nyq + (size_t)m * W2 * ROW_NYQ;
@@ -355,7 +436,8 @@ __global__ void dpdrho_kernel(const double* __restrict__ base, int nlines, int n
 template <int NT1, int NT2>
 static int launch_geometry(const GeoParams& p, cudaStream_t st) {
     auto kern = geometry_kernel<NT1, NT2>;
-    const size_t smem = 16 + ((size_t)p.M1 * (2 * NT1 + 1) * ROW_MN + (size_t)p.M2 * (2 * NT2 + 1) * ROW_NYQ) * sizeof(double);
+    const size_t e_mn = (NT1 > 0) ? (size_t)(NT1 + 1) * ROWP_MN : (size_t)ROW_MN, e_nyq = (NT2 > 0) ? (size_t)(NT2 + 1) * ROWP_NYQ : (size_t)ROW_NYQ;
+    const size_t smem = 16 + ((size_t)p.M1 * e_mn + (size_t)p.M2 * e_nyq) * sizeof(double);
     if (smem > 200 * 1024) { set_error("Fourier tables of one surface do not fit in shared memory"); return IBS_ERR_UNSUPPORTED; }
     static bool configured = false;
     if (!configured) {
@@ -411,7 +493,8 @@ int geometry_dispatch(const double* tab_mn, const double* tab_nyq, const double*
     if (NT1 > 0 && M1 > MAX_M_NEWTON) { set_error("mpol too large for a 3-D equilibrium"); return IBS_ERR_UNSUPPORTED; }
 
     // ---- workspace: packed tables (stream-ordered allocation) + cached device copy of the mode indices
-    const size_t n_mn = (size_t)ns * M1 * W1 * ROW_MN, n_nyq = (size_t)ns * M2 * W2 * ROW_NYQ;
+    const size_t n_mn = (size_t)ns * M1 * (NT1 > 0 ? (size_t)(NT1 + 1) * ROWP_MN : (size_t)W1 * ROW_MN);
+    const size_t n_nyq = (size_t)ns * M2 * (NT2 > 0 ? (size_t)(NT2 + 1) * ROWP_NYQ : (size_t)W2 * ROW_NYQ);
     double* pk = nullptr; int* d_idx = nullptr;
     {
         // The mode layout of an equilibrium family never changes between calls: keep the last one on
