@@ -128,3 +128,17 @@ def test_chain_length_divides():
     from ideal_ballooning_solver_b200 import scan
     assert scan.chain_length(64) == 16 and scan.chain_length(15) == 15 and scan.chain_length(24) == 12
     assert scan.chain_length(1) == 1 and scan.chain_length(17) == 1 and scan.chain_length(32) == 16
+
+
+def test_ballooning_penalty_matches_reference_formula():
+    """sims_runner_NCSX.py:254-261, 313."""
+    from ideal_ballooning_solver_b200 import penalty
+    gam = np.array([-1e-3, -2e-4, -1e-4, 3e-4, 0.0])
+    want = 50 * np.sum(np.maximum(gam - (-0.0002), 0.0))
+    assert penalty.ballooning_penalty(gam) == want
+    assert penalty.objective(0.25, gam) == np.sqrt(0.25 + want)
+    assert penalty.objective(0.25, gam, converged=False) == np.sqrt(9999.0)
+    gams = np.stack([gam, gam + 1e-5, gam - 2e-5])
+    f, df = penalty.fd_jacobian([0.25, 0.26, 0.24], gams, np.array([0.0, 1e-3, 2e-3]))
+    assert df.shape == (1, 3) and df[0, 0] == 0
+    np.testing.assert_allclose(df[0, 1], (f[1] - f[0]) / 1e-3 * 0.5 / np.sqrt(f[0]))
