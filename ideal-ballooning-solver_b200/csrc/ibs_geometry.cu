@@ -51,8 +51,8 @@ struct GeoParams {
 // ---- pack kernels: (ns, rows, mn) tables -> dense (m, n_idx) grid with the n-weights folded in -----------
 __global__ void pack_mn_kernel(const double* __restrict__ tab, const int* __restrict__ mode_m, const int* __restrict__ mode_n,
                                int ns, int mnmax, int M1, int W1, int NT1, int nfp, double* __restrict__ out) {
-    const int s = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.x;                                   // surfaces on x (up to 2^31 - 1 of them)
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
     if (k >= mnmax) return;
     const int m = mode_m[k], nn = mode_n[k];          // nn = n / nfp
     const double* t = tab + (size_t)s * 6 * mnmax;
@@ -73,8 +73,8 @@ __global__ void pack_mn_kernel(const double* __restrict__ tab, const int* __rest
 }
 __global__ void pack_nyq_kernel(const double* __restrict__ tab, const int* __restrict__ mode_m, const int* __restrict__ mode_n,
                                 int ns, int mnmax, int M2, int W2, int NT2, int nfp, double* __restrict__ out) {
-    const int s = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.x;                                   // surfaces on x (up to 2^31 - 1 of them)
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
     if (k >= mnmax) return;
     const int m = mode_m[k], nn = mode_n[k];
     const double* t = tab + (size_t)s * 7 * mnmax;
@@ -515,8 +515,8 @@ int geometry_dispatch(const double* tab_mn, const double* tab_nyq, const double*
     keep_pool_cached();
     IBS_CUDA_CHECK(cudaMallocAsync((void**)&pk, (n_mn + n_nyq) * sizeof(double), st));
     IBS_CUDA_CHECK(cudaMemsetAsync(pk, 0, (n_mn + n_nyq) * sizeof(double), st));
-    pack_mn_kernel<<<dim3((mnmax + 127) / 128, ns), 128, 0, st>>>(tab_mn, d_idx, d_idx + mnmax, ns, mnmax, M1, W1, NT1, nfp, pk);
-    pack_nyq_kernel<<<dim3((mnmax_nyq + 127) / 128, ns), 128, 0, st>>>(tab_nyq, d_idx + 2 * mnmax, d_idx + 2 * mnmax + mnmax_nyq, ns,
+    pack_mn_kernel<<<dim3(ns, (mnmax + 127) / 128), 128, 0, st>>>(tab_mn, d_idx, d_idx + mnmax, ns, mnmax, M1, W1, NT1, nfp, pk);
+    pack_nyq_kernel<<<dim3(ns, (mnmax_nyq + 127) / 128), 128, 0, st>>>(tab_nyq, d_idx + 2 * mnmax, d_idx + 2 * mnmax + mnmax_nyq, ns,
                                                                      mnmax_nyq, M2, W2, NT2, nfp, pk + n_mn);
     IBS_CUDA_CHECK(cudaGetLastError());
 
