@@ -59,8 +59,16 @@ __device__ __forceinline__ double pow2i(int e) {            // 2^e, e clamped to
 __device__ __forceinline__ unsigned sign_word(double v) { return (unsigned)__double2hiint(v); }
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
-__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(FULL, v, d); }
-__device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_down_sync(FULL, v, d); }
+// 64-bit shuffles as two explicit 32-bit shuffles (lo first): with the library overload for double ptxas allocates
+// the halves in swapped order and then swaps them back with three XORs per value.
+__device__ __forceinline__ double shfl_up_d(double v, int d) {
+    const int lo = __shfl_up_sync(FULL, __double2loint(v), d), hi = __shfl_up_sync(FULL, __double2hiint(v), d);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_down_d(double v, int d) {
+    const int lo = __shfl_down_sync(FULL, __double2loint(v), d), hi = __shfl_down_sync(FULL, __double2hiint(v), d);
+    return __hiloint2double(hi, lo);
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
