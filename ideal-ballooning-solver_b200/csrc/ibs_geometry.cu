@@ -92,36 +92,6 @@ __global__ void pack_nyq_kernel(const double* __restrict__ tab, const int* __res
     }
 }
 
-// ---- TMA bulk copy global -> shared, completion on an mbarrier -------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(dst)),
-                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-    unsigned done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    }
-}
-
 // cos/sin(m theta - n phi) for one n_idx with compile-time sign
 template <int SGN> __device__ __forceinline__ void angle(double cm, double sm, double cn, double sn, double& ca, double& sa) {
     if (SGN >= 0) { ca = fma(cm, cn, sm * sn); sa = fma(sm, cn, -(cm * sn)); }      // n >= 0: m th - |n| ph
