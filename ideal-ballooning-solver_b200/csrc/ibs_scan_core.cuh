@@ -36,7 +36,8 @@ constexpr int MAXLEV = 3;         // coarse levels (strides 2, 4, 8)
 constexpr int MIN_COARSE_N = 65;  // a level is used only if it has at least this many points
 constexpr int MAXIT_LEVEL = 64;   // evaluations per level before giving up
 constexpr int K_MARGIN = 8;       // matching row kept this far from both ends
-constexpr double LOWQ = 1.0e3;    // max|z| / |z_k| above which the matching row is moved (see solve_item)
+constexpr double LOWQ = 1.0e3;
+constexpr int PEAK_SNAP = 16;      // a coarsest-level peak within Nl / PEAK_SNAP rows of the middle keeps the middle matching row    // max|z| / |z_k| above which the matching row is moved (see solve_item)
 
 constexpr int FLAG_NOT_CONVERGED = 1, FLAG_BAD_INPUT = 2, FLAG_SIGMA_NOT_MAX = 4;   // = IBS_FLAG_* of include/ibs_b200.h
 
@@ -155,6 +156,78 @@ IBS_HD int sign_changes32(unsigned m, unsigned enter_sign) {     // bit (31 - i)
 #endif
 }
 
+IBS_HD int sign_changes_n(unsigned m, int n, unsigned enter_sign) {   // n <= 32 steps recorded; bit (n-1-i) = sign after step i
+    const unsigned pm = (n >= 32) ? 0x7fffffffu : ((1u << (n - 1)) - 1u);
+    const unsigned v = (m ^ (m >> 1)) & pm;
+#if defined(__CUDA_ARCH__)
+    return __popc(v) + (int)(((m >> (n - 1)) & 1u) ^ enter_sign);
+#else
+    return __builtin_popcount(v) + (int)(((m >> (n - 1)) & 1u) ^ enter_sign);
+#endif
+}
+
+// ---- software-pipelined form of the chain steps ------------------------------------------------------------------
+// ptxas keeps the source order of a loop body almost unchanged and a warp issues in order, so the fast paths are
+// written as a pipeline by hand: the records of step i+2 are loaded, the coefficients of step i+1 are formed and the
+// chains of step i are advanced in ONE interleaved instruction stream (forward and backward statements alternate),
+// so that neither the shared-memory latency nor the 8-cycle DFMA latency is exposed.
+struct Co { double a, t, F; };        // of the row being stepped to: a = g + g_prev (= 2 gh of the half cell), t', F'
+
+IBS_HD void coef_next(const Rec& r, double th0, double lam, double& gp, Co& c) {
+    const double g = fma(th0, fma(th0, r.G2, r.G1), r.G0);
+    const double C = fma(th0, r.C1, r.C0);
+    c.F = g * r.R;
+    c.a = g + gp;
+    gp = g;
+    c.t = fma(-lam, c.F, C);
+}
+IBS_HD void fwd_chain(const Co& c, double& X, double& W, double& S) {
+    const double Xn = fma(c.a, X, W);
+    W = fma(-c.t, Xn, c.a * W);
+    S = fma(c.F * Xn, Xn, (c.a * c.a) * S);
+    X = Xn;
+}
+IBS_HD void bwd_chain(const Co& c, double& X, double& W, double& S, double& tcur) {
+    const double tmp = fma(tcur, X, W);
+    const double Xn = fma(c.a, X, -tmp);
+    W = c.a * tmp;
+    S = fma(c.F * Xn, Xn, (c.a * c.a) * S);
+    X = Xn;
+    tcur = c.t;
+}
+// chains of the current joint step (coefficients cf, cb) + coefficients of the next one from the records nf, nb
+IBS_HD void joint_step(const Rec& nf, const Rec& nb, double th0, double lam, Co& cf, Co& cb, double& gf, double& gb,
+                       double& Xf, double& Wf, double& Sf, double& Xb, double& Wb, double& Sb, double& tb) {
+    const double p1 = fma(th0, nf.G2, nf.G1);
+    const double XnF = fma(cf.a, Xf, Wf);
+    const double p2 = fma(th0, nb.G2, nb.G1);
+    const double tmp = fma(tb, Xb, Wb);
+    const double CF = fma(th0, nf.C1, nf.C0);
+    const double aWF = cf.a * Wf;
+    const double CB = fma(th0, nb.C1, nb.C0);
+    const double a2F = cf.a * cf.a;
+    const double gF = fma(th0, p1, nf.G0);
+    const double XnB = fma(cb.a, Xb, -tmp);
+    const double gB = fma(th0, p2, nb.G0);
+    Wf = fma(-cf.t, XnF, aWF);
+    const double a2B = cb.a * cb.a;
+    Wb = cb.a * tmp;
+    const double FXF = cf.F * XnF;
+    const double a2SF = a2F * Sf;
+    const double FFn = gF * nf.R;
+    const double FXB = cb.F * XnB;
+    const double FBn = gB * nb.R;
+    const double a2SB = a2B * Sb;
+    Sf = fma(FXF, XnF, a2SF);
+    Sb = fma(FXB, XnB, a2SB);
+    tb = cb.t;
+    Xf = XnF; Xb = XnB;
+    cf.a = gF + gf; gf = gF; cf.F = FFn;
+    cb.a = gB + gb; gb = gB; cb.F = FBn;
+    cf.t = fma(-lam, FFn, CF);
+    cb.t = fma(-lam, FBn, CB);
+}
+
 // One evaluation at the shifts lam[]: twisted residual r' (= 2 r), S' = sum 2F z^2 (z_k = 1), node count.
 // rho = lam + r' / S' is the Rayleigh quotient of z; #eigenvalues above lam = nodes + (r' > 0).
 template <int SPL, class Ctx>
@@ -186,32 +259,47 @@ IBS_HD void eval_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL]
             }
             i0 = 2;
         }
-        if (s > 0 && TR * s + TR - 1 < qmin) {
-            // fast path: a whole tile of both directions, no per-step tests; node counts from sign histories
+        if (TR * s + TR - 1 < qmin) {
+            // fast path (pipelined): the rest of the tile in both directions, no per-step tests; node counts from sign histories
+            Co cf[SPL], cb[SPL];
             unsigned mf[SPL], mb[SPL], ef[SPL], eb[SPL];
+            {
+                const Rec f = load_rec(ctx.frec(i0)), b = load_rec(ctx.brec(i0));
 #pragma unroll
-            for (int q = 0; q < SPL; ++q) { mf[q] = 0; mb[q] = 0; ef[q] = sign_bit(Xf[q]); eb[q] = sign_bit(Xb[q]); }
-#pragma unroll 1
-            for (int hh = 0; hh < TR; hh += 16) {
-#pragma unroll 2
-                for (int ii = 0; ii < 16; ++ii) {
-                    const Rec rf = load_rec(ctx.frec(hh + ii)), rb = load_rec(ctx.brec(hh + ii));
-#pragma unroll
-                    for (int q = 0; q < SPL; ++q) {
-                        fwd_step(rf, th0[q], lam[q], Xf[q], Wf[q], Sf[q], gf[q]);
-                        mf[q] = (mf[q] << 1) | sign_bit(Xf[q]);
-                        bwd_step<true>(rb, th0[q], lam[q], Xb[q], Wb[q], Sb[q], gb[q], tb[q]);
-                        mb[q] = (mb[q] << 1) | sign_bit(Xb[q]);
-                    }
+                for (int q = 0; q < SPL; ++q) {
+                    coef_next(f, th0[q], lam[q], gf[q], cf[q]);
+                    coef_next(b, th0[q], lam[q], gb[q], cb[q]);
+                    mf[q] = 0; mb[q] = 0; ef[q] = sign_bit(Xf[q]); eb[q] = sign_bit(Xb[q]);
                 }
+            }
+            Rec rf = load_rec(ctx.frec(i0 + 1)), rb = load_rec(ctx.brec(i0 + 1));
+#pragma unroll 2
+            for (int i = i0; i < TR - 1; ++i) {
+                const Rec nf = load_rec(ctx.frec(i + 2)), nb = load_rec(ctx.brec(i + 2));      // (slot 32 of the last step: unused)
 #pragma unroll
-                for (int q = 0; q < SPL; ++q) { rescale3(Xf[q], Wf[q], Sf[q]); rescale3(Xb[q], Wb[q], Sb[q]); }
+                for (int q = 0; q < SPL; ++q) {
+                    joint_step(rf, rb, th0[q], lam[q], cf[q], cb[q], gf[q], gb[q], Xf[q], Wf[q], Sf[q], Xb[q], Wb[q], Sb[q], tb[q]);
+                    mf[q] = (mf[q] << 1) | sign_bit(Xf[q]);
+                    mb[q] = (mb[q] << 1) | sign_bit(Xb[q]);
+                }
+                if ((i & 15) == 15) {
+#pragma unroll
+                    for (int q = 0; q < SPL; ++q) { rescale3(Xf[q], Wf[q], Sf[q]); rescale3(Xb[q], Wb[q], Sb[q]); }
+                }
+                rf = nf; rb = nb;
             }
 #pragma unroll
-            for (int q = 0; q < SPL; ++q) nodes[q] += sign_changes32(mf[q], ef[q]) + sign_changes32(mb[q], eb[q]);
+            for (int q = 0; q < SPL; ++q) {          // last step of the tile: its coefficients are ready
+                fwd_chain(cf[q], Xf[q], Wf[q], Sf[q]);
+                bwd_chain(cb[q], Xb[q], Wb[q], Sb[q], tb[q]);
+                mf[q] = (mf[q] << 1) | sign_bit(Xf[q]);
+                mb[q] = (mb[q] << 1) | sign_bit(Xb[q]);
+                rescale3(Xf[q], Wf[q], Sf[q]); rescale3(Xb[q], Wb[q], Sb[q]);
+                nodes[q] += sign_changes_n(mf[q], TR - i0, ef[q]) + sign_changes_n(mb[q], TR - i0, eb[q]);
+            }
         } else {
 #pragma unroll 1
-            for (int i = i0; i < TR; ++i) {
+            for (int i = i0; i < TR && TR * s + i <= qmax; ++i) {
                 const int qq = TR * s + i;
                 if (qq <= qf_end) {
                     const Rec rf = load_rec(ctx.frec(i));
@@ -248,52 +336,56 @@ IBS_HD void eval_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL]
     }
 }
 
-// ---- output passes (plain recurrence with reciprocals: the un-scaled eigenfunction is needed) ------------
+// ---- output pass (plain recurrence with reciprocals: the un-scaled eigenfunction is needed) ---------------
 // One direction of one solve.  The window holds the four previous rows' values; the sums are split by row parity
 // (Simpson weights 4/3 and 2/3) and carry the running power-of-two scale 2^-E of x.
 struct Sweep {
     double x, w; int E;
-    double W1, W2, W3, W4;        // x of the previous rows: W1 = the row computed last, ... (running scale; O2: normalised X)
+    double W1, W2, W3, W4;        // x of the previous rows: W1 = the row computed last, ... (running scale)
     double gp, gpp;               // g of the last row and of the one before
     double tcur;                  // backward: t' of the current row
-    double a0[2], a1[2], aD[2];   // sum t' X^2, sum F' X^2, sum g D^2 by row parity
+    double a0e, a0o, a1e, a1o, aDe, aDo;   // sum t' X^2, sum F' X^2, sum g D^2 of the even / odd rows (no dynamic indexing)
     double aEnd;                  // g D^2 of the Dirichlet end point
     double vmax; int jmax;        // largest |x| so far (running scale) and its row
     bool bad;
+    double fsc, cn; int ex;       // writing pass: X = x * fsc, fsc = cn 2^ex (ex follows the rescalings)
 };
 
-struct SolveOut {                 // what the first output pass returns per solve
+struct SolveOut {                 // what the output pass returns per solve
     double gam, zmax; int jmax; bool bad;
-    double xkf, xkb; int Ekf, Ekb;
-    double Dm1, D0, Dp1;          // seam stencils (z scale): rows k-1, k, k+1
+    double xkf, xkb; int Ekf, Ekb;     // the two sweeps at the matching row: value and scale exponent
 };
 
 constexpr double C23 = 2.0 / 3.0, C12 = 1.0 / 12.0;
+constexpr int EBLK = 16;          // rows between two rescalings
 
 template <bool WRITE>
-IBS_HD void sweep_rescale(Sweep& sw, double& fsc, double cnorm, int& ex) {
+IBS_HD void sweep_rescale(Sweep& sw) {
     const int e = exp_max2(sw.x, sw.w);
     const double s = pow2(-e);
     sw.x *= s; sw.w *= s; sw.E += e;
-    if (!WRITE) {
+    if (WRITE) {
+        sw.ex += e;
+        sw.fsc = sw.cn * pow2(sw.ex);
+    } else {
         const double s2 = s * s;
         sw.W1 *= s; sw.W2 *= s; sw.W3 *= s; sw.W4 *= s;
-        sw.a0[0] *= s2; sw.a0[1] *= s2; sw.a1[0] *= s2; sw.a1[1] *= s2; sw.aD[0] *= s2; sw.aD[1] *= s2; sw.aEnd *= s2;
+        sw.a0e *= s2; sw.a0o *= s2; sw.a1e *= s2; sw.a1o *= s2; sw.aDe *= s2; sw.aDo *= s2; sw.aEnd *= s2;
         sw.vmax *= s;
-    } else {
-        ex += e;
-        fsc = cnorm * pow2(ex);
     }
 }
 
-// normalised output value: the largest element must come out as exactly 1 (utils.py:1605 divides by the maximum)
-IBS_HD double norm_clamp(double v) { return (fabs(v) > 1.0 - 1e-15) ? copysign(1.0, v) : v; }
+// Normalised output value.  The largest element must come out as exactly 1 (utils.py:1605 divides by the maximum):
+// the scale factor is inflated by a few ulp (NORM_INFLATE) and the product clamped from above.
+constexpr double NORM_INFLATE = 1.0 + 1.7763568394002505e-15;      // 1 + 2^-49
+IBS_HD double norm_value(double x, double fsc) { return fmin(x * fsc, 1.0); }
 
-// One step of an output pass for one direction.  DIR = +1 forward (new row = qq), -1 backward (new row = Nl-1-qq).
-// `last` (backward only): the step that reaches row k (its X^2 terms and its X belong to the forward sweep).
+// One step of the output pass for one direction, general form (first rows, last rows, unequal chains).
+// DIR = +1 forward (new row = qq), -1 backward (new row = Nl-1-qq).  `last` (backward only): the step that reaches
+// row k (its X^2 terms and its X belong to the forward sweep).  WRITE: the normalised X goes to Xw (if not null) and
+// nothing is summed.
 template <int DIR, bool WRITE>
-IBS_HD void out_step(Sweep& sw, const Rec& rc, double th0, double lam, int qq, int Nl, bool last, double fsc, double ih,
-                     double* Xrow, double* dXrow) {
+IBS_HD void out_step(Sweep& sw, const Rec& rc, double th0, double lam, int qq, int Nl, bool last, double* Xw) {
     double g, C, F;
     coef(rc, th0, g, C, F);
     const double a = g + sw.gp;
@@ -305,74 +397,150 @@ IBS_HD void out_step(Sweep& sw, const Rec& rc, double th0, double lam, int qq, i
     if (DIR > 0) { xn = fma(sw.w, ia, sw.x); sw.w = fma(-tnew, xn, sw.w); }
     else         { sw.w = fma(sw.tcur, sw.x, sw.w); xn = fma(-sw.w, ia, sw.x); sw.tcur = tnew; }
     sw.x = xn;
-    const int par = qq & 1;                    // = parity of the row (N odd)
-    double v = xn;                             // value entering the window
     if (WRITE) {
-        v = norm_clamp(xn * fsc);
-        if (Xrow && !last) Xrow[row] = v;
-    } else {
-        if (!last) {
-            const double x2 = xn * xn;
-            sw.a0[par] = fma(tnew, x2, sw.a0[par]);
-            sw.a1[par] = fma(F, x2, sw.a1[par]);
-            const double ax = fabs(xn);
-            if (ax > sw.vmax) { sw.vmax = ax; sw.jmax = row; }
-        }
+        if (!last && Xw) Xw[row] = norm_value(xn, sw.fsc);
+        sw.gp = g;
+        return;
     }
-    // stencil of the row two behind (h-free: D = h dX)
+    const int par = qq & 1;                    // = parity of the row (N odd)
+    if (!last) {
+        const double x2 = xn * xn;
+        if (par) { sw.a0o = fma(tnew, x2, sw.a0o); sw.a1o = fma(F, x2, sw.a1o); }
+        else     { sw.a0e = fma(tnew, x2, sw.a0e); sw.a1e = fma(F, x2, sw.a1e); }
+        const double ax = fabs(xn);
+        if (ax > sw.vmax) { sw.vmax = ax; sw.jmax = row; }
+    }
+    // stencil of the row two behind (h-free: D = h dX; only D^2 is needed here)
     if (qq >= 4) {
-        const double D = fma(C23, sw.W1 - sw.W3, -(C12 * (v - sw.W4)));     // forward orientation; backward: -D
-        if (WRITE) { if (dXrow) dXrow[(DIR > 0) ? row - 2 : row + 2] = ((DIR > 0) ? D : -D) * ih; }
-        else sw.aD[par] = fma(sw.gpp, D * D, sw.aD[par]);
+        const double D = fma(C23, sw.W1 - sw.W3, -(C12 * (xn - sw.W4)));
+        if (par) sw.aDo = fma(sw.gpp, D * D, sw.aDo); else sw.aDe = fma(sw.gpp, D * D, sw.aDe);
     } else if (qq == 2) {
-        // Dirichlet end point: one-sided formula (utils.py:1610, 1613), weight 1/3
-        const double D = fma(2.0, sw.W1, -0.5 * v);                     // forward: dX_0 h;  backward: -dX_{N-1} h
-        if (WRITE) { if (dXrow) dXrow[(DIR > 0) ? 0 : Nl - 1] = ((DIR > 0) ? D : -D) * ih; }
-        else sw.aEnd = sw.gpp * D * D;
+        const double D = fma(2.0, sw.W1, -0.5 * xn);        // Dirichlet end point: one-sided formula (utils.py:1610, 1613), weight 1/3
+        sw.aEnd = sw.gpp * D * D;
     } else if (qq == 3) {
-        // rows 1 and N-2: second-order formula (utils.py:1611-1612)
-        const double D = 0.5 * sw.W1;                                   // forward: dX_1 h = X_2 / 2;  backward: -dX_{N-2} h
-        if (WRITE) { if (dXrow) dXrow[(DIR > 0) ? 1 : Nl - 2] = ((DIR > 0) ? D : -D) * ih; }
-        else sw.aD[par] = fma(sw.gpp, D * D, sw.aD[par]);
+        const double D = 0.5 * sw.W1;                       // rows 1 and N-2: second-order formula (utils.py:1611-1612)
+        sw.aDo = fma(sw.gpp, D * D, sw.aDo);
     }
-    sw.W4 = sw.W3; sw.W3 = sw.W2; sw.W2 = sw.W1; sw.W1 = v;
+    sw.W4 = sw.W3; sw.W3 = sw.W2; sw.W2 = sw.W1; sw.W1 = xn;
     sw.gpp = sw.gp; sw.gp = g;
 }
 
 IBS_HD void sweep_zero(Sweep& sw) {
     sw.E = 0; sw.W1 = sw.W2 = sw.W3 = sw.W4 = 0.0; sw.tcur = 0.0;
-    sw.a0[0] = sw.a0[1] = sw.a1[0] = sw.a1[1] = sw.aD[0] = sw.aD[1] = 0.0; sw.aEnd = 0.0;
+    sw.a0e = sw.a0o = sw.a1e = sw.a1o = sw.aDe = sw.aDo = 0.0; sw.aEnd = 0.0;
     sw.vmax = 0.0; sw.jmax = 0; sw.bad = false;
+}
+
+// ---- pipelined form of the output-pass step (interior rows: generic stencil, never the last backward step) -----
+struct OCo { double ia, t, F, g; };   // of the row being stepped to: 1 / (g + g_prev), t', F', g
+
+// chain + tail of one direction for the row whose coefficients are c (PAR = parity of the row, compile time)
+template <int DIR, int PAR, bool WRITE>
+IBS_HD void out_chain_tail(Sweep& sw, const OCo& c, int row, double* Xw) {
+    double xn;
+    if (DIR > 0) { xn = fma(sw.w, c.ia, sw.x); sw.w = fma(-c.t, xn, sw.w); }
+    else         { sw.w = fma(sw.tcur, sw.x, sw.w); xn = fma(-sw.w, c.ia, sw.x); sw.tcur = c.t; }
+    sw.x = xn;
+    if (WRITE) {
+        if (Xw) Xw[row] = norm_value(xn, sw.fsc);
+        sw.gp = c.g;
+        return;
+    }
+    const double d1 = sw.W1 - sw.W3;
+    const double x2 = xn * xn;
+    const double d2 = xn - sw.W4;
+    const double ax = fabs(xn);
+    if (PAR) { sw.a0o = fma(c.t, x2, sw.a0o); sw.a1o = fma(c.F, x2, sw.a1o); }
+    else     { sw.a0e = fma(c.t, x2, sw.a0e); sw.a1e = fma(c.F, x2, sw.a1e); }
+    const double D = fma(C23, d1, -(C12 * d2));
+    if (ax > sw.vmax) { sw.vmax = ax; sw.jmax = row; }
+    const double D2 = D * D;
+    if (PAR) sw.aDo = fma(sw.gpp, D2, sw.aDo); else sw.aDe = fma(sw.gpp, D2, sw.aDe);
+    sw.W4 = sw.W3; sw.W3 = sw.W2; sw.W2 = sw.W1; sw.W1 = xn;
+    sw.gpp = sw.gp; sw.gp = c.g;
+}
+
+// coefficients (with the reciprocal) of the next row of one direction, not interleaved (prologue of a tile)
+template <bool WRITE>
+IBS_HD void out_coef(const Rec& r, double th0, double lam, double gprev, OCo& c, bool& bad) {
+    double C;
+    coef(r, th0, c.g, C, c.F);
+    const double a = c.g + gprev;
+    if (!WRITE) bad |= not_pos_normal(a) | not_pos_normal(c.F) | not_finite(C);
+    c.ia = rcp_fast(a);
+    c.t = fma(-lam, c.F, C);
+}
+
+// One joint step: chains + tails of the current rows (coefficients cf, cb) and, interleaved with them, the
+// coefficients of the next rows from the records nf, nb (the two reciprocal chains are the long dependences).
+template <int PAR, bool WRITE>
+IBS_HD void out_joint(const Rec& nf, const Rec& nb, double th0, double lam, OCo& cf, OCo& cb, Sweep& f, Sweep& b, int qq, int Nl,
+                      double* Xw) {
+    // next coefficients, part 1: g, a and the reciprocal seeds
+    const double pA = fma(th0, nf.G2, nf.G1);
+    const double pB = fma(th0, nb.G2, nb.G1);
+    const double CA = fma(th0, nf.C1, nf.C0);
+    const double CB = fma(th0, nb.C1, nb.C0);
+    const double gA = fma(th0, pA, nf.G0);
+    const double gB = fma(th0, pB, nb.G0);
+    const double aA = gA + cf.g;
+    const double aB = gB + cb.g;
+#if defined(__CUDA_ARCH__)
+    double rA, rB;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rA) : "d"(aA));
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rB) : "d"(aB));
+#else
+    double rA = 1.0 / aA, rB = 1.0 / aB;
+#endif
+    const double FA = gA * nf.R;
+    const double FB = gB * nb.R;
+    if (!WRITE) {
+        f.bad |= not_pos_normal(aA) | not_pos_normal(FA) | not_finite(CA);
+        b.bad |= not_pos_normal(aB) | not_pos_normal(FB) | not_finite(CB);
+    }
+    // current forward row
+    out_chain_tail<+1, PAR, WRITE>(f, cf, qq, Xw);
+    // next coefficients, part 2: first Newton step of the reciprocals (cubic)
+    double eA = fma(-aA, rA, 1.0);
+    double eB = fma(-aB, rB, 1.0);
+    const double tA = fma(-lam, FA, CA);
+    const double tB = fma(-lam, FB, CB);
+    eA = fma(eA, eA, eA);
+    eB = fma(eB, eB, eB);
+    rA = fma(rA, eA, rA);
+    rB = fma(rB, eB, rB);
+    // current backward row
+    out_chain_tail<-1, PAR, WRITE>(b, cb, Nl - 1 - qq, Xw);
+    // next coefficients, part 3: second Newton step
+#if defined(__CUDA_ARCH__)
+    eA = fma(-aA, rA, 1.0);
+    eB = fma(-aB, rB, 1.0);
+    rA = fma(rA, eA, rA);
+    rB = fma(rB, eB, rB);
+#endif
+    cf.ia = rA; cf.t = tA; cf.F = FA; cf.g = gA;
+    cb.ia = rB; cb.t = tB; cb.F = FB; cb.g = gB;
 }
 
 // Output pass at the shifts lam[] with matching row k.
 //   WRITE = false: Simpson Rayleigh quotient gam (utils.py:1605-1621), max|z| and its row, validity -> out[]
-//   WRITE = true : X = z / max z (and dX) written for the solves with wr[q] set, using out[] of the first pass
+//   WRITE = true : the chains are recomputed (bit-identically) and X = z / max|z| is written to Xw[q] (where not null),
+//                  using the scales out[] of the first pass
 template <int SPL, bool WRITE, class Ctx>
-IBS_HD void out_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL], const double (&lam)[SPL], double h,
-                     SolveOut (&out)[SPL], const bool (&wr)[SPL], double* const (&Xrow_in)[SPL], double* const (&dXrow_in)[SPL]) {
+IBS_HD void out_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL], const double (&lam)[SPL],
+                     SolveOut (&out)[SPL], double* const (&Xw)[SPL]) {
     const int qf_end = k, qb_end = Nl - 1 - k;
     const int qmin = imin(qf_end, qb_end), qmax = imax(qf_end, qb_end);
     const int nst = qmax / TR + 1;
-    const double ih = 1.0 / h;
     ctx.begin_pass(lev, Nl, k, nst);
     Sweep F_[SPL], B_[SPL];
-    double fscf[SPL], fscb[SPL], cnf[SPL], cnb[SPL];
-    int exf[SPL], exb[SPL];
-    double* Xrow[SPL]; double* dXrow[SPL];
+    auto rescale_all = [&](bool do_f, bool do_b) {
 #pragma unroll
-    for (int q = 0; q < SPL; ++q) {
-        Xrow[q] = (WRITE && wr[q]) ? Xrow_in[q] : nullptr;
-        dXrow[q] = (WRITE && wr[q]) ? dXrow_in[q] : nullptr;
-        fscf[q] = fscb[q] = cnf[q] = cnb[q] = 0.0; exf[q] = exb[q] = 0;
-        if (WRITE) {
-            const bool ok = !out[q].bad && out[q].zmax > 0.0 && out[q].zmax < 1e300;
-            cnf[q] = ok ? 1.0 / (out[q].xkf * out[q].zmax) : 0.0;
-            cnb[q] = ok ? 1.0 / (out[q].xkb * out[q].zmax) : 0.0;
-            exf[q] = -out[q].Ekf; exb[q] = -out[q].Ekb;
-            fscf[q] = cnf[q] * pow2(exf[q]); fscb[q] = cnb[q] * pow2(exb[q]);
+        for (int q = 0; q < SPL; ++q) {
+            if (do_f) sweep_rescale<WRITE>(F_[q]);
+            if (do_b) sweep_rescale<WRITE>(B_[q]);
         }
-    }
+    };
     for (int s = 0; s < nst; ++s) {
         ctx.wait(s);
         int i0 = 0;
@@ -384,103 +552,160 @@ IBS_HD void out_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL],
                 double g, C, Fv;
                 Sweep& f = F_[q]; Sweep& b = B_[q];
                 sweep_zero(f); sweep_zero(b);
+                if (WRITE) {
+                    const bool ok = !out[q].bad && out[q].zmax > 0.0 && out[q].zmax < 1e300;
+                    f.cn = ok ? NORM_INFLATE / (out[q].xkf * out[q].zmax) : 0.0;
+                    b.cn = ok ? NORM_INFLATE / (out[q].xkb * out[q].zmax) : 0.0;
+                    f.ex = -out[q].Ekf; b.ex = -out[q].Ekb;
+                    f.fsc = f.cn * pow2(f.ex); b.fsc = b.cn * pow2(b.ex);
+                    if (Xw[q]) { Xw[q][0] = 0.0; Xw[q][Nl - 1] = 0.0; }
+                }
                 // forward: row 0 (x = 0, w' = 1), then the ordinary step to row 1
                 coef(f0, th0[q], g, C, Fv);
                 f.x = 0.0; f.w = 1.0; f.gp = g; f.gpp = g;
-                if (WRITE) { if (Xrow[q]) { Xrow[q][0] = 0.0; Xrow[q][Nl - 1] = 0.0; } }
-                out_step<+1, WRITE>(f, f1, th0[q], lam[q], 1, Nl, false, fscf[q], ih, Xrow[q], dXrow[q]);
+                out_step<+1, WRITE>(f, f1, th0[q], lam[q], 1, Nl, false, Xw[q]);
                 // backward: row N-1 (x = 0), row M = N-2 with x = 1, w' = -a_M
                 coef(b0, th0[q], g, C, Fv);
                 const double gN = g;
                 coef(b1, th0[q], g, C, Fv);
                 const double a = g + gN;
-                if (!WRITE) b.bad |= not_pos_normal(a) | not_pos_normal(Fv) | not_finite(C);
                 b.x = 1.0; b.w = -a; b.gp = g; b.gpp = gN; b.tcur = fma(-lam[q], Fv, C);
-                double v = 1.0;
-                if (WRITE) { v = norm_clamp(fscb[q]); if (Xrow[q]) Xrow[q][Nl - 2] = v; }
-                else { b.a0[1] = b.tcur; b.a1[1] = Fv; b.vmax = 1.0; b.jmax = Nl - 2; }
-                b.W1 = v;
+                if (WRITE) { if (Xw[q]) Xw[q][Nl - 2] = norm_value(1.0, b.fsc); }
+                else {
+                    b.bad |= not_pos_normal(a) | not_pos_normal(Fv) | not_finite(C);
+                    b.a0o = b.tcur; b.a1o = Fv; b.vmax = 1.0; b.jmax = Nl - 2;
+                    b.W1 = 1.0;
+                }
             }
             i0 = 2;
-        }
-        if (s > 0 && TR * s + TR - 1 < qmin) {
-#pragma unroll 1
-            for (int hh = 0; hh < TR; hh += 16) {
-#pragma unroll 2
-                for (int ii = 0; ii < 16; ++ii) {
-                    const int qq = TR * s + hh + ii;
-                    const Rec rf = load_rec(ctx.frec(hh + ii)), rb = load_rec(ctx.brec(hh + ii));
+            if (TR - 1 < qmin) {
+                // rows 2 and 3 (and N-3, N-4) have their own stencils: general step; the rest of the tile is pipelined
+                for (; i0 < 4; ++i0) {
+                    const Rec rf = load_rec(ctx.frec(i0)), rb = load_rec(ctx.brec(i0));
 #pragma unroll
                     for (int q = 0; q < SPL; ++q) {
-                        out_step<+1, WRITE>(F_[q], rf, th0[q], lam[q], qq, Nl, false, fscf[q], ih, Xrow[q], dXrow[q]);
-                        out_step<-1, WRITE>(B_[q], rb, th0[q], lam[q], qq, Nl, false, fscb[q], ih, Xrow[q], dXrow[q]);
+                        out_step<+1, WRITE>(F_[q], rf, th0[q], lam[q], i0, Nl, false, Xw[q]);
+                        out_step<-1, WRITE>(B_[q], rb, th0[q], lam[q], i0, Nl, false, Xw[q]);
                     }
                 }
+            }
+        }
+        if (TR * s + TR - 1 < qmin) {
+            // fast path (pipelined, interior rows): coefficients one step ahead, records two steps ahead; i0 is even
+            const int q0 = TR * s;
+            OCo cf[SPL], cb[SPL];
+            {
+                const Rec f0 = load_rec(ctx.frec(i0)), b0 = load_rec(ctx.brec(i0));
 #pragma unroll
                 for (int q = 0; q < SPL; ++q) {
-                    sweep_rescale<WRITE>(F_[q], fscf[q], cnf[q], exf[q]);
-                    sweep_rescale<WRITE>(B_[q], fscb[q], cnb[q], exb[q]);
+                    out_coef<WRITE>(f0, th0[q], lam[q], F_[q].gp, cf[q], F_[q].bad);
+                    out_coef<WRITE>(b0, th0[q], lam[q], B_[q].gp, cb[q], B_[q].bad);
                 }
             }
+            Rec rf = load_rec(ctx.frec(i0 + 1)), rb = load_rec(ctx.brec(i0 + 1));
+#pragma unroll 1
+            for (int i = i0; i < TR - 2; i += 2) {
+                const Rec nf = load_rec(ctx.frec(i + 2)), nb = load_rec(ctx.brec(i + 2));
+#pragma unroll
+                for (int q = 0; q < SPL; ++q)
+                    out_joint<0, WRITE>(rf, rb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], q0 + i, Nl, Xw[q]);
+                rf = load_rec(ctx.frec(i + 3)); rb = load_rec(ctx.brec(i + 3));
+#pragma unroll
+                for (int q = 0; q < SPL; ++q)
+                    out_joint<1, WRITE>(nf, nb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], q0 + i + 1, Nl, Xw[q]);
+                if (i == EBLK - 2) rescale_all(true, true);
+            }
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) {
+                // step 30 (its successor's coefficients from the record of step 31), then step 31 on its own
+                out_joint<0, WRITE>(rf, rb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], q0 + TR - 2, Nl, Xw[q]);
+                out_chain_tail<+1, 1, WRITE>(F_[q], cf[q], q0 + TR - 1, Xw[q]);
+                out_chain_tail<-1, 1, WRITE>(B_[q], cb[q], Nl - 1 - (q0 + TR - 1), Xw[q]);
+            }
+            rescale_all(true, true);
         } else {
 #pragma unroll 1
-            for (int i = i0; i < TR; ++i) {
+            for (int i = i0; i < TR && TR * s + i <= qmax; ++i) {
                 const int qq = TR * s + i;
                 if (qq <= qf_end) {
                     const Rec rf = load_rec(ctx.frec(i));
 #pragma unroll
-                    for (int q = 0; q < SPL; ++q)
-                        out_step<+1, WRITE>(F_[q], rf, th0[q], lam[q], qq, Nl, false, fscf[q], ih, Xrow[q], dXrow[q]);
+                    for (int q = 0; q < SPL; ++q) out_step<+1, WRITE>(F_[q], rf, th0[q], lam[q], qq, Nl, false, Xw[q]);
                 }
                 if (qq <= qb_end) {
                     const Rec rb = load_rec(ctx.brec(i));
 #pragma unroll
-                    for (int q = 0; q < SPL; ++q)
-                        out_step<-1, WRITE>(B_[q], rb, th0[q], lam[q], qq, Nl, qq == qb_end, fscb[q], ih, Xrow[q], dXrow[q]);
+                    for (int q = 0; q < SPL; ++q) out_step<-1, WRITE>(B_[q], rb, th0[q], lam[q], qq, Nl, qq == qb_end, Xw[q]);
                 }
-                if ((i & 15) == 15) {
-#pragma unroll
-                    for (int q = 0; q < SPL; ++q) {
-                        if (qq < qf_end) sweep_rescale<WRITE>(F_[q], fscf[q], cnf[q], exf[q]);      // a finished sweep keeps its final scale
-                        if (qq < qb_end) sweep_rescale<WRITE>(B_[q], fscb[q], cnb[q], exb[q]);
-                    }
-                }
+                if ((i & (EBLK - 1)) == EBLK - 1) rescale_all(qq < qf_end, qq < qb_end);       // a finished sweep keeps its final scale
             }
         }
         ctx.release(s);
     }
+    if (WRITE) return;
     // ---- seam (rows k-1, k, k+1) and totals
 #pragma unroll
     for (int q = 0; q < SPL; ++q) {
         const Sweep& f = F_[q]; const Sweep& b = B_[q];
-        if (!WRITE) {
-            SolveOut& o = out[q];
-            o.xkf = f.x; o.xkb = b.x; o.Ekf = f.E; o.Ekb = b.E;
-            o.bad = f.bad | b.bad;
-            const double zf = 1.0 / f.x, zb = 1.0 / b.x;
-            // window values in the z scale: forward W1..W4 = rows k..k-3, backward W1..W4 = rows k..k+3
-            const double Zm3 = f.W4 * zf, Zm2 = f.W3 * zf, Zm1 = f.W2 * zf, Zp1 = b.W2 * zb, Zp2 = b.W3 * zb, Zp3 = b.W4 * zb;
-            o.Dm1 = fma(C23, 1.0 - Zm2, -(C12 * (Zp1 - Zm3)));
-            o.D0 = fma(C23, Zp1 - Zm1, -(C12 * (Zp2 - Zm2)));
-            o.Dp1 = fma(C23, Zp2 - 1.0, -(C12 * (Zp3 - Zm1)));
-            const double w43 = 4.0 / 3.0, w23 = 2.0 / 3.0, w13 = 1.0 / 3.0;
-            const double wk = (k & 1) ? w43 : w23, wk1 = (k & 1) ? w23 : w43;       // rows k and k +- 1
-            const double zf2 = zf * zf, zb2 = zb * zb;
-            const double sD = zf2 * (w43 * f.aD[1] + w23 * f.aD[0] + w13 * f.aEnd) + zb2 * (w43 * b.aD[1] + w23 * b.aD[0] + w13 * b.aEnd) +
-                              wk1 * (f.gpp * o.Dm1 * o.Dm1 + b.gpp * o.Dp1 * o.Dp1) + wk * (f.gp * o.D0 * o.D0);
-            const double sX0 = zf2 * (w43 * f.a0[1] + w23 * f.a0[0]) + zb2 * (w43 * b.a0[1] + w23 * b.a0[0]);
-            const double sX1 = zf2 * (w43 * f.a1[1] + w23 * f.a1[0]) + zb2 * (w43 * b.a1[1] + w23 * b.a1[0]);
-            o.gam = lam[q] + (sX0 - 2.0 * sD) / sX1;
-            const double mf = f.vmax * fabs(zf), mb = b.vmax * fabs(zb);
-            o.zmax = fmax(mf, mb);
-            o.jmax = (mb > mf) ? b.jmax : f.jmax;
-            if (!(o.zmax == o.zmax)) o.zmax = 1e308;          // NaN: treat as unusable
-        } else if (dXrow[q]) {
-            // the seam stencils in the normalised scale (the windows hold normalised X here)
-            const double Xm3 = f.W4, Xm2 = f.W3, Xm1 = f.W2, X0 = f.W1, Xp1 = b.W2, Xp2 = b.W3, Xp3 = b.W4;
-            dXrow[q][k - 1] = fma(C23, X0 - Xm2, -(C12 * (Xp1 - Xm3))) * ih;
-            dXrow[q][k] = fma(C23, Xp1 - Xm1, -(C12 * (Xp2 - Xm2))) * ih;
-            dXrow[q][k + 1] = fma(C23, Xp2 - X0, -(C12 * (Xp3 - Xm1))) * ih;
+        SolveOut& o = out[q];
+        o.xkf = f.x; o.xkb = b.x; o.Ekf = f.E; o.Ekb = b.E;
+        o.bad = f.bad | b.bad;
+        const double zf = 1.0 / f.x, zb = 1.0 / b.x;
+        // window values in the z scale: forward W1..W4 = rows k..k-3, backward W1..W4 = rows k..k+3
+        const double Zm3 = f.W4 * zf, Zm2 = f.W3 * zf, Zm1 = f.W2 * zf, Zp1 = b.W2 * zb, Zp2 = b.W3 * zb, Zp3 = b.W4 * zb;
+        const double Dm1 = fma(C23, 1.0 - Zm2, -(C12 * (Zp1 - Zm3)));
+        const double D0 = fma(C23, Zp1 - Zm1, -(C12 * (Zp2 - Zm2)));
+        const double Dp1 = fma(C23, Zp2 - 1.0, -(C12 * (Zp3 - Zm1)));
+        const double w43 = 4.0 / 3.0, w23 = 2.0 / 3.0, w13 = 1.0 / 3.0;
+        const double wk = (k & 1) ? w43 : w23, wk1 = (k & 1) ? w23 : w43;       // rows k and k +- 1
+        const double zf2 = zf * zf, zb2 = zb * zb;
+        const double sD = zf2 * (w43 * f.aDo + w23 * f.aDe + w13 * f.aEnd) + zb2 * (w43 * b.aDo + w23 * b.aDe + w13 * b.aEnd) +
+                          wk1 * (f.gpp * Dm1 * Dm1 + b.gpp * Dp1 * Dp1) + wk * (f.gp * D0 * D0);
+        const double sX0 = zf2 * (w43 * f.a0o + w23 * f.a0e) + zb2 * (w43 * b.a0o + w23 * b.a0e);
+        const double sX1 = zf2 * (w43 * f.a1o + w23 * f.a1e) + zb2 * (w43 * b.a1o + w23 * b.a1e);
+        o.gam = lam[q] + (sX0 - 2.0 * sD) / sX1;
+        const double mf = f.vmax * fabs(zf), mb = b.vmax * fabs(zb);
+        o.zmax = fmax(mf, mb);
+        o.jmax = (mb > mf) ? b.jmax : f.jmax;
+        if (!(o.zmax == o.zmax)) o.zmax = 1e308;          // NaN: treat as unusable
+    }
+}
+
+// Finish the eigenfunction output of ONE solve with the rows dealt out over `nl` cooperating lanes (coalesced):
+// zero_X: X = 0 (invalid input);  dX (if not null) from the normalised X by the reference's stencils (utils.py:1610-1614).
+// ld/sync come from the context (the rows were written by other lanes).
+template <class Ctx>
+IBS_HD void fixup_solve(Ctx& ctx, double* X, double* dX, int N, bool zero_X, double h, int lane, int nl) {
+    if (zero_X)
+        for (int j = lane; j < N; j += nl) X[j] = 0.0;
+    if (dX) {
+        ctx.sync_mem();
+        const double c23h = 2.0 / (3.0 * h), i12h = 1.0 / (12.0 * h), i2h = 1.0 / (2.0 * h), ih = 1.0 / h;
+        constexpr int UD = 4;                  // rows per lane whose loads are in flight together
+        for (int j0 = lane; j0 < N; j0 += UD * nl) {
+            double xm2[UD], xm1[UD], xp1[UD], xp2[UD];
+#pragma unroll
+            for (int u = 0; u < UD; ++u) {
+                const int j = j0 + u * nl;
+                const bool in = j < N;
+                xm2[u] = (in && j >= 2) ? ctx.ld(X + j - 2) : 0.0;
+                xm1[u] = (in && j >= 1) ? ctx.ld(X + j - 1) : 0.0;
+                xp1[u] = (in && j + 1 < N) ? ctx.ld(X + j + 1) : 0.0;
+                xp2[u] = (in && j + 2 < N) ? ctx.ld(X + j + 2) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < UD; ++u) {
+                const int j = j0 + u * nl;
+                if (j < N) {
+                    double d;
+                    if (j == 0) d = (2.0 * xp1[u] - 0.5 * xp2[u]) * ih;                    // X_0 = 0 (utils.py:1610)
+                    else if (j == 1) d = xp1[u] * i2h;                                       // (X_2 - X_0) / 2h
+                    else if (j == N - 2) d = -xm1[u] * i2h;                                  // (X_{N-1} - X_{N-3}) / 2h
+                    else if (j == N - 1) d = (0.5 * xm2[u] - 2.0 * xm1[u]) * ih;             // utils.py:1613
+                    else d = c23h * (xp1[u] - xm1[u]) - (xp2[u] - xm2[u]) * i12h;
+                    dX[j] = d;
+                }
+            }
         }
     }
 }
@@ -562,139 +787,159 @@ struct ItemProblem {
 struct ItemResult { double gam, rho; int info; };
 
 // Everything for the SPL solves of one lane.  act[q] = false: the slot duplicates a valid solve and writes nothing.
+// Written as a state machine with ONE call site per kind of pass (iteration / output pass), so that the kernel holds
+// a single copy of each streaming loop (instruction cache).
+//   ITER   bracketed Rayleigh-quotient iteration on level `lev`, coarsest first; start = Richardson estimate of the
+//          two coarser levels' eigenvalues
+//   PEAK   (coarsest level only) first output pass there: the lanes' eigenfunction peaks give the matching row
+//   O1     fine level: Simpson Rayleigh quotient, max|z|, validity;  solves with |z_k| << max|z| are re-converged
+//          with the matching row moved to their peak (at most three times) before they are accepted
+//          then X (stored raw by O1) is normalised and dX formed by the context's fix-up (coalesced over the rows)
+//   SIGMA  one count at 2 sigma - lambda (utils.py:1597 returns the eigenvalue nearest sigma; the engine lambda_max)
+enum { PH_ITER = 0, PH_PEAK = 1, PH_O1 = 2, PH_SIGMA = 4 };
+
 template <int SPL, class Ctx>
 IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL], const bool (&act)[SPL], const double (&sigma)[SPL],
                        const bool has_sigma, double* const (&Xrow)[SPL], double* const (&dXrow)[SPL], ItemResult (&res)[SPL]) {
+    // Xrow[q]: the solve's X row (needed, as scratch, also when only dX is wanted)
     const double scale = fmax(fabs(P.U), 1e-3);
     const double tol = 1.7763568394002505e-15 * scale, tol_stag = 1e-10 * scale;
-    Iter it[SPL];
-    double lam_eval[SPL], r[SPL], S[SPL], rho1[SPL], rho2[SPL];
-    int nodes[SPL], nev[SPL], flags[SPL];
     const double qnan = NAN;
-#pragma unroll
-    for (int q = 0; q < SPL; ++q) { rho1[q] = qnan; rho2[q] = qnan; nev[q] = 0; flags[q] = 0; }
-    int k = 0;
+    const int N = P.N;
+    Iter it[SPL];
+    double sh[SPL], r[SPL], S[SPL], rho1[SPL], rho2[SPL];     // sh: the shifts of the next pass
+    int nodes[SPL], nev[SPL], flags[SPL];
+    bool fin[SPL], wr[SPL], need[SPL];
     SolveOut out[SPL];
-    bool nowr[SPL];
+    double* Xraw[SPL];
+    const bool want_out = P.want_X || P.want_dX;
 #pragma unroll
-    for (int q = 0; q < SPL; ++q) nowr[q] = false;
-    double* nullrow[SPL];
+    for (int q = 0; q < SPL; ++q) {
+        Xraw[q] = nullptr;
+        rho1[q] = qnan; rho2[q] = qnan; nev[q] = 0; flags[q] = 0; fin[q] = false; wr[q] = false; need[q] = false;
+        res[q].gam = qnan; res[q].rho = qnan;
+        iter_init(it[q], qnan, P.Lb, P.U, false);
+        sh[q] = it[q].lam;
+    }
+    int lev = P.nlev, Nl = level_n(N, lev), k = clamp_k((Nl - 1) / 2, Nl), round = 0, phase = PH_ITER;
+    bool lowq_any = false;
+    int jsel = -1;
+    for (;;) {
+        if (phase == PH_ITER || phase == PH_SIGMA) {
+            eval_pass<SPL>(ctx, lev, Nl, k, th0, sh, r, S, nodes);
+            if (phase == PH_SIGMA) {
 #pragma unroll
-    for (int q = 0; q < SPL; ++q) nullrow[q] = nullptr;
-
-    for (int lev = P.nlev; lev >= 0; --lev) {
-        const int Nl = level_n(P.N, lev);
-        k = (lev == P.nlev) ? clamp_k((Nl - 1) / 2, Nl) : clamp_k(2 * k, Nl);
-        const double stop = (lev > 0) ? 1e-7 * scale : tol;
-#pragma unroll
-        for (int q = 0; q < SPL; ++q) {
-            double l0 = rho1[q];
-            if (rho2[q] == rho2[q]) l0 = rho1[q] - 0.25 * (rho2[q] - rho1[q]);      // Richardson: the error is ~ h^2
-            iter_init(it[q], l0, P.Lb, P.U, false);
-        }
-        for (;;) {
-#pragma unroll
-            for (int q = 0; q < SPL; ++q) lam_eval[q] = it[q].lam;
-            eval_pass<SPL>(ctx, lev, Nl, k, th0, lam_eval, r, S, nodes);
+                for (int q = 0; q < SPL; ++q)
+                    if (need[q] && nodes[q] + (r[q] > 0.0 ? 1 : 0) > 1) flags[q] |= FLAG_SIGMA_NOT_MAX;
+                break;
+            }
             bool alldone = true;
 #pragma unroll
             for (int q = 0; q < SPL; ++q) {
                 if (!it[q].done) ++nev[q];
-                iter_update(it[q], r[q], S[q], nodes[q], P.U, tol, tol_stag, stop, lev == 0);
+                iter_update(it[q], r[q], S[q], nodes[q], P.U, tol, tol_stag, (lev > 0) ? 1e-7 * scale : tol, lev == 0);
                 alldone &= it[q].done;
+                sh[q] = it[q].lam;
             }
-            if (ctx.all(alldone)) break;
-        }
+            if (!ctx.all(alldone)) continue;
+            // ---- this level has converged
+            if (lev > 0) {
 #pragma unroll
-        for (int q = 0; q < SPL; ++q) { rho2[q] = rho1[q]; rho1[q] = (it[q].conv && it[q].rho == it[q].rho) ? it[q].rho : qnan; }
-        if (lev == P.nlev && lev > 0) {
-            // matching row from the coarsest eigenfunctions: the middle of the range of the lanes' peaks
-            double sh[SPL];
+                for (int q = 0; q < SPL; ++q) { rho2[q] = rho1[q]; rho1[q] = (it[q].conv && it[q].rho == it[q].rho) ? it[q].rho : qnan; }
+                if (lev == P.nlev) {
 #pragma unroll
-            for (int q = 0; q < SPL; ++q) sh[q] = (rho1[q] == rho1[q]) ? rho1[q] : it[q].lam;
-            out_pass<SPL, false>(ctx, lev, Nl, k, th0, sh, P.h, out, nowr, nullrow, nullrow);
+                    for (int q = 0; q < SPL; ++q) sh[q] = (rho1[q] == rho1[q]) ? rho1[q] : it[q].lam;
+                    phase = PH_PEAK;
+                    continue;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < SPL; ++q)
+                    if (!fin[q]) {
+                        sh[q] = (it[q].conv && it[q].rho == it[q].rho) ? it[q].rho : it[q].lam;
+                        if (!it[q].conv) flags[q] |= FLAG_NOT_CONVERGED;
+                    }
+                phase = PH_O1;
+                continue;
+            }
+        } else if (phase == PH_PEAK) {
+            // matching row from the coarsest eigenfunctions: the middle of the range of the lanes' peaks -- unless that is
+            // close to the middle row, which keeps the two chains equally long (everything on the fast path)
+            out_pass<SPL, false>(ctx, lev, Nl, k, th0, sh, out, Xraw);
             int jlo = 1 << 30, jhi = -1;
 #pragma unroll
             for (int q = 0; q < SPL; ++q) { jlo = imin(jlo, out[q].jmax); jhi = imax(jhi, out[q].jmax); }
             jlo = ctx.min_i(jlo); jhi = ctx.max_i(jhi);
-            k = clamp_k((jlo + jhi) / 2, Nl);
-        }
-    }
-    // ---- fine level done: output passes; the matching row is moved if some solve has |z_k| << max|z|
-    const int N = P.N;
-    bool fin[SPL];
-    double shift[SPL];
-#pragma unroll
-    for (int q = 0; q < SPL; ++q) {
-        fin[q] = false;
-        shift[q] = (it[q].conv && it[q].rho == it[q].rho) ? it[q].rho : it[q].lam;
-        if (!it[q].conv) flags[q] |= FLAG_NOT_CONVERGED;
-        res[q].gam = qnan; res[q].rho = qnan;
-    }
-    for (int round = 0; round < 4; ++round) {
-        out_pass<SPL, false>(ctx, 0, N, k, th0, shift, P.h, out, nowr, nullrow, nullrow);
-        bool newly[SPL], lowq_any = false, wr_any = false;
-        int jsel = -1;
-#pragma unroll
-        for (int q = 0; q < SPL; ++q) {
-            const bool lowq = !fin[q] && !out[q].bad && out[q].zmax > LOWQ && round < 3;
-            newly[q] = !fin[q] && !lowq;
-            if (newly[q]) {
-                fin[q] = true;
-                res[q].gam = out[q].bad ? qnan : out[q].gam;
-                res[q].rho = out[q].bad ? qnan : shift[q];
-                if (out[q].bad) flags[q] = FLAG_BAD_INPUT;
-            }
-            if (lowq && jsel < 0) jsel = out[q].jmax;
-            lowq_any |= lowq;
-            wr_any |= newly[q] && act[q];
-        }
-        if ((P.want_X || P.want_dX) && ctx.any(wr_any)) {
-            bool wr[SPL];
-#pragma unroll
-            for (int q = 0; q < SPL; ++q) wr[q] = newly[q] && act[q];
-            out_pass<SPL, true>(ctx, 0, N, k, th0, shift, P.h, out, wr, Xrow, dXrow);
-        }
-        if (!ctx.any(lowq_any)) break;
-        // move the matching row to the peak of the first low-quality solve and re-converge those solves there
-        k = clamp_k(ctx.first_i(jsel), N);
-#pragma unroll
-        for (int q = 0; q < SPL; ++q) iter_init(it[q], shift[q], P.Lb, P.U, fin[q]);
-        for (;;) {
-#pragma unroll
-            for (int q = 0; q < SPL; ++q) lam_eval[q] = it[q].lam;
-            eval_pass<SPL>(ctx, 0, N, k, th0, lam_eval, r, S, nodes);
-            bool alldone = true;
+            const int kp = (jlo + jhi) / 2, km = (Nl - 1) / 2;
+            k = clamp_k((kp > km ? kp - km : km - kp) * PEAK_SNAP <= Nl ? km : kp, Nl);
+        } else if (phase == PH_O1) {
+            out_pass<SPL, false>(ctx, 0, N, k, th0, sh, out, Xraw);
+            bool wr_any = false, fix_any = false;
+            lowq_any = false; jsel = -1;
 #pragma unroll
             for (int q = 0; q < SPL; ++q) {
-                if (!it[q].done) ++nev[q];
-                iter_update(it[q], r[q], S[q], nodes[q], P.U, tol, tol_stag, tol, true);
-                alldone &= it[q].done;
+                const bool lowq = !fin[q] && !out[q].bad && out[q].zmax > LOWQ && round < 3;
+                const bool newly = !fin[q] && !lowq;
+                if (newly) {
+                    fin[q] = true;
+                    res[q].gam = out[q].bad ? qnan : out[q].gam;
+                    res[q].rho = out[q].bad ? qnan : sh[q];
+                    if (out[q].bad) flags[q] = FLAG_BAD_INPUT;
+                }
+                if (lowq && jsel < 0) jsel = out[q].jmax;
+                lowq_any |= lowq;
+                wr[q] = newly && act[q];
+                wr_any |= wr[q];
+                fix_any |= wr[q] && (out[q].bad || P.want_dX);
             }
-            if (ctx.all(alldone)) break;
-        }
+            ++round;
+            if (want_out && ctx.any(wr_any)) {
+                // second pass: X of the solves accepted in this round (invalid ones are zero-filled by the fix-up)
 #pragma unroll
-        for (int q = 0; q < SPL; ++q)
-            if (!fin[q]) {
-                shift[q] = (it[q].conv && it[q].rho == it[q].rho) ? it[q].rho : it[q].lam;
-                if (!it[q].conv) flags[q] |= FLAG_NOT_CONVERGED;
+                for (int q = 0; q < SPL; ++q) Xraw[q] = (wr[q] && !out[q].bad) ? Xrow[q] : nullptr;
+                out_pass<SPL, true>(ctx, 0, N, k, th0, sh, out, Xraw);
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) Xraw[q] = nullptr;
+                if (ctx.any(fix_any)) ctx.template fixup<SPL>(wr, Xrow, dXrow, N, out, P.h, P.want_dX);
             }
-    }
-    // ---- nearest-sigma check (utils.py:1597 returns the eigenvalue nearest sigma; the engine returns lambda_max)
-    if (has_sigma) {
-        bool need[SPL], any_need = false;
+        }
+        // ---- what follows a finished level (lev > 0), the peak finder, or the output passes of a round
+        if (lev > 0) {
+            --lev;
+            Nl = level_n(N, lev);
+            k = clamp_k(2 * k, Nl);
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) {
+                double l0 = rho1[q];
+                if (rho2[q] == rho2[q]) l0 = rho1[q] - 0.25 * (rho2[q] - rho1[q]);      // Richardson: the error is ~ h^2
+                iter_init(it[q], l0, P.Lb, P.U, false);
+                sh[q] = it[q].lam;
+            }
+            phase = PH_ITER;
+            continue;
+        }
+        if (ctx.any(lowq_any)) {
+            // move the matching row to the peak of the first low-quality solve and re-converge the open solves there
+            k = clamp_k(ctx.first_i(jsel), N);
+            lowq_any = false;
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) {
+                iter_init(it[q], sh[q], P.Lb, P.U, fin[q]);
+                if (!fin[q]) sh[q] = it[q].lam;
+            }
+            phase = PH_ITER;
+            continue;
+        }
+        if (!has_sigma) break;
+        bool any_need = false;
 #pragma unroll
         for (int q = 0; q < SPL; ++q) {
-            need[q] = (flags[q] & FLAG_BAD_INPUT) == 0 && sigma[q] < shift[q];
-            lam_eval[q] = need[q] ? 2.0 * sigma[q] - shift[q] : shift[q];
+            need[q] = (flags[q] & FLAG_BAD_INPUT) == 0 && sigma[q] < sh[q];
+            if (need[q]) sh[q] = 2.0 * sigma[q] - sh[q];
             any_need |= need[q];
         }
-        if (ctx.any(any_need)) {
-            eval_pass<SPL>(ctx, 0, N, k, th0, lam_eval, r, S, nodes);
-#pragma unroll
-            for (int q = 0; q < SPL; ++q)
-                if (need[q] && nodes[q] + (r[q] > 0.0 ? 1 : 0) > 1) flags[q] |= FLAG_SIGMA_NOT_MAX;
-        }
+        if (!ctx.any(any_need)) break;
+        phase = PH_SIGMA;
     }
 #pragma unroll
     for (int q = 0; q < SPL; ++q) {

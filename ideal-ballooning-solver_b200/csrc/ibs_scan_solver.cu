@@ -1,0 +1,324 @@
+// K2+K3 for scan-shaped batches: lane-per-solve kernel (see ibs_scan_core.cuh for the algorithm).
+//
+// Replaces the theta0 loop around gamma_ball_full (/root/reference/ball_scan.py:262-274, utils.py:1550-1624) for
+// batches in which every field line is solved for a row of theta0 values.
+//   scan_prep_kernel   one CTA per field line: the six theta0-independent coefficient rows of the line as 48-byte
+//                      records, for the fine grid and up to three coarser ones (every 2nd/4th/8th point), scaled by a
+//                      power of two so that max g ~ 1; bounds of the spectrum valid for the line's whole theta0 range
+//   scan_solve_kernel  persistent warps; a warp takes (line, group of 32*SPL theta0) items from a global counter.
+//                      The records are streamed through a per-warp ring of shared-memory tiles with TMA bulk copies
+//                      (cp.async.bulk + mbarrier, 3 stages ahead); every lane reads the SAME record (broadcast LDS.128)
+//                      and advances its own solve(s).  No shuffles, no block barriers, no per-solve set-up; HBM
+//                      traffic is the records once (they stay in L2 for the ~10 passes of an item) plus the outputs.
+#include <cstdlib>
+
+#include "ibs_common.cuh"
+#include "ibs_scan_core.cuh"
+
+namespace ibs {
+using namespace scan;
+
+constexpr int SC_NSTAGE = 4;                       // pipeline stages per warp
+constexpr int SC_TILE = TR * REC;                  // doubles per tile (1536 B)
+constexpr int SC_STAGE = 2 * SC_TILE;              // forward + backward tile
+constexpr int SC_RING = SC_NSTAGE * SC_STAGE;      // doubles per warp (12 KB)
+constexpr int SC_WARPS = 4;                        // warps per CTA (they never synchronise with each other)
+#ifndef IBS_SCAN_CTAS1
+#define IBS_SCAN_CTAS1 2      // CTAs per SM the SPL = 1 kernel is compiled for (register cap 65536 / (128 * CTAS))
+#endif
+
+struct ScanParams {
+    const double* poly;       // [nline][rows_total][REC]
+    const double* bounds;     // [nline][2]: U, Lb
+    const double* theta0;     // [nline * nth0]
+    const double* sigma;      // nullable
+    int nline, nth0, N, nlev, rows_total, groups, nitems;
+    double h;
+    double* lam_out; double* lam_matrix_out; double* X_out; double* dX_out; int* info_out;
+    double* X_rows;           // where the eigenfunctions go: X_out, or scratch when only dX is wanted (null: no eigenfunction output)
+    unsigned* counter;
+};
+
+// ---- device context: record streaming + warp votes --------------------------------------------------
+struct DevCtx {
+    double* ring; uint64_t* bars; unsigned parity; int lane;
+    const double* line_base; int N;
+    const double* lvl; int Nl, nst, qf_end, qb_end;
+    const double* tf; const double* tb;
+
+    __device__ __forceinline__ void issue(int s) {          // lane 0
+        const int slot = s % SC_NSTAGE;
+        double* dstf = ring + slot * SC_STAGE;
+        double* dstb = dstf + SC_TILE;
+        const int f0 = TR * s;
+        const int fn = (f0 <= qf_end) ? min(TR, Nl - f0) : 0;
+        const int b1 = Nl - TR * s;
+        const int b0 = max(0, b1 - TR);
+        const int bn = (TR * s <= qb_end) ? (b1 - b0) : 0;
+        mbar_expect_tx(&bars[slot], (unsigned)((fn + bn) * REC * sizeof(double)));
+        if (fn) tma_bulk_g2s(dstf, lvl + (size_t)f0 * REC, (unsigned)(fn * REC * sizeof(double)), &bars[slot]);
+        if (bn) tma_bulk_g2s(dstb + (TR - bn) * REC, lvl + (size_t)b0 * REC, (unsigned)(bn * REC * sizeof(double)), &bars[slot]);
+    }
+    __device__ __forceinline__ void begin_pass(int lev, int Nl_, int k, int nst_) {
+        lvl = line_base + (size_t)level_offset(N, lev) * REC;
+        Nl = Nl_; nst = nst_; qf_end = k; qb_end = Nl_ - 1 - k;
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const int n0 = nst < SC_NSTAGE ? nst : SC_NSTAGE;
+            for (int s = 0; s < n0; ++s) issue(s);
+        }
+    }
+    __device__ __forceinline__ void wait(int s) {
+        const int slot = s % SC_NSTAGE;
+        // bounded spin: a pipeline bug must trap, not hang the device
+        const unsigned addr = (unsigned)__cvta_generic_to_shared(&bars[slot]), par = (parity >> slot) & 1u;
+        unsigned done = 0, spins = 0;
+        while (!done) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(done) : "r"(addr), "r"(par) : "memory");
+            if (!done && ++spins > (1u << 24)) __trap();
+        }
+        parity ^= 1u << slot;
+        tf = ring + slot * SC_STAGE;
+        tb = tf + SC_TILE;
+    }
+    __device__ __forceinline__ const double* frec(int i) const { return tf + i * REC; }
+    __device__ __forceinline__ const double* brec(int i) const { return tb + (TR - 1 - i) * REC; }
+    __device__ __forceinline__ void release(int s) {
+        __syncwarp();                                        // every lane has consumed the stage
+        if (lane == 0 && s + SC_NSTAGE < nst) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(s + SC_NSTAGE);
+        }
+    }
+    __device__ __forceinline__ bool all(bool b) const { return __all_sync(FULL, b); }
+    __device__ __forceinline__ bool any(bool b) const { return __any_sync(FULL, b); }
+    __device__ __forceinline__ int min_i(int v) const { return __reduce_min_sync(FULL, v); }
+    __device__ __forceinline__ int max_i(int v) const { return __reduce_max_sync(FULL, v); }
+    __device__ __forceinline__ int first_i(int v) const {   // v of the first lane with v >= 0 (at least one exists)
+        const unsigned m = __ballot_sync(FULL, v >= 0);
+        return __shfl_sync(FULL, v, m ? (__ffs(m) - 1) : 0);
+    }
+    // the fix-up reads rows that OTHER lanes of the warp have written: L2 loads after a warp-level fence
+    __device__ __forceinline__ void sync_mem() const { __syncwarp(); }
+    __device__ __forceinline__ double ld(const double* p) const { return __ldcg(p); }
+    // zero-fill invalid solves / form dX of the solves flagged wr[]: one solve at a time, its rows dealt out over the 32 lanes
+    template <int SPL>
+    __device__ __forceinline__ void fixup(const bool (&wr)[SPL], double* const (&Xrow)[SPL], double* const (&dXrow)[SPL], int N_,
+                                          const SolveOut (&out)[SPL], double h, bool want_dX) {
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) {
+            unsigned m = __ballot_sync(FULL, wr[q] && (out[q].bad || want_dX));
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const bool bad = __shfl_sync(FULL, (int)out[q].bad, l) != 0;
+                double* X = reinterpret_cast<double*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(Xrow[q]), l));
+                double* dX = reinterpret_cast<double*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(dXrow[q]), l));
+                fixup_solve(*this, X, want_dX ? dX : nullptr, N_, bad, h, lane, 32);
+            }
+        }
+        __syncwarp();
+    }
+};
+
+template <int SPL>
+__global__ void __launch_bounds__(SC_WARPS * 32, (SPL == 1) ? IBS_SCAN_CTAS1 : 2)
+scan_solve_kernel(const ScanParams p) {
+    extern __shared__ __align__(128) double sc_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DevCtx ctx;
+    ctx.ring = sc_smem + warp * SC_RING;
+    ctx.bars = reinterpret_cast<uint64_t*>(sc_smem + SC_WARPS * SC_RING) + warp * SC_NSTAGE;
+    ctx.parity = 0; ctx.lane = lane; ctx.N = p.N;
+    if (lane == 0) {
+        for (int s = 0; s < SC_NSTAGE; ++s) mbar_init(&ctx.bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int N = p.N;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(p.counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= p.nitems) break;
+        const int line = item / p.groups, grp = item - line * p.groups;
+        double th0[SPL], sg[SPL];
+        bool act[SPL];
+        double* Xrow[SPL]; double* dXrow[SPL];
+        size_t sidx[SPL];
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) {
+            const int idx = grp * (32 * SPL) + q * 32 + lane;
+            act[q] = idx < p.nth0;
+            sidx[q] = (size_t)line * p.nth0 + (act[q] ? idx : p.nth0 - 1);
+            th0[q] = p.theta0[sidx[q]];
+            sg[q] = p.sigma ? p.sigma[sidx[q]] : 0.0;
+            Xrow[q] = (act[q] && p.X_rows) ? p.X_rows + sidx[q] * N : nullptr;
+            dXrow[q] = (act[q] && p.dX_out) ? p.dX_out + sidx[q] * N : nullptr;
+        }
+        ItemProblem P;
+        P.N = N; P.nlev = p.nlev; P.h = p.h; P.U = p.bounds[2 * line]; P.Lb = p.bounds[2 * line + 1];
+        P.want_X = p.X_rows != nullptr; P.want_dX = p.dX_out != nullptr;
+        ctx.line_base = p.poly + (size_t)line * p.rows_total * REC;
+        ItemResult res[SPL];
+        solve_item<SPL>(ctx, P, th0, act, sg, p.sigma != nullptr, Xrow, dXrow, res);
+#pragma unroll
+        for (int q = 0; q < SPL; ++q)
+            if (act[q]) {
+                p.lam_out[sidx[q]] = res[q].gam;
+                if (p.lam_matrix_out) p.lam_matrix_out[sidx[q]] = res[q].rho;
+                if (p.info_out) p.info_out[sidx[q]] = res[q].info;
+            }
+    }
+}
+
+// ---- preparation: one CTA per field line ----------------------------------------------------------------
+constexpr int PREP_T = 256;
+
+template <class Op>
+__device__ __forceinline__ double block_reduce(double v, Op op, double* scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(FULL, v, o));
+    __syncthreads();                                       // scratch free
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double a = scratch[0];
+    for (int w = 1; w < PREP_T / 32; ++w) a = op(a, scratch[w]);
+    return a;
+}
+struct PMax { __device__ __forceinline__ double operator()(double a, double b) const { return fmax(a, b); } };
+struct PMin { __device__ __forceinline__ double operator()(double a, double b) const { return fmin(a, b); } };
+
+__global__ void __launch_bounds__(PREP_T)
+scan_prep_kernel(const double* __restrict__ base, const double* __restrict__ dPdrho, const double* __restrict__ theta0, int nth0,
+                 int N, double h2, int nlev, int rows_total, double* __restrict__ poly, double* __restrict__ bounds) {
+    __shared__ double scratch[PREP_T / 32];
+    const int line = blockIdx.x, tid = threadIdx.x;
+    const double* b = base + (size_t)line * IBS_NBASE * N;
+    const double dP = dPdrho[line];
+    double t0 = 1e300, t1 = -1e300;
+    for (int i = tid; i < nth0; i += PREP_T) { const double t = theta0[(size_t)line * nth0 + i]; t0 = fmin(t0, t); t1 = fmax(t1, t); }
+    t0 = block_reduce(t0, PMin(), scratch);
+    t1 = block_reduce(t1, PMax(), scratch);
+    auto record = [&](int j) {
+        return raw_record(b[(size_t)IBS_BASE_BMAG * N + j], b[(size_t)IBS_BASE_GRADPAR * N + j], b[(size_t)IBS_BASE_CVDRIFT * N + j],
+                          b[(size_t)IBS_BASE_CVDRIFT0 * N + j], b[(size_t)IBS_BASE_GDS2 * N + j], b[(size_t)IBS_BASE_GDS21 * N + j],
+                          b[(size_t)IBS_BASE_GDS22 * N + j], dP, h2);
+    };
+    double gmax = 0.0;
+    for (int j = tid; j < N; j += PREP_T) {
+        const Rec r = record(j);
+        double gmn, gmx, cmn, cmx;
+        record_ranges(r, t0, t1, gmn, gmx, cmn, cmx);
+        if (gmx > gmax) gmax = gmx;
+    }
+    gmax = block_reduce(gmax, PMax(), scratch);
+    const double sg = (gmax > 0.0 && gmax < 1e300) ? pow2(-exp_max2(gmax, 0.0)) : 1.0;
+    double U = -1e300, minC = 1e300, maxg = 0.0, minF = 1e300, maxF = 0.0;
+    double* out = poly + (size_t)line * rows_total * REC;
+    for (int j = tid; j < N; j += PREP_T) {
+        Rec r = record(j);
+        r.G0 *= sg; r.G1 *= sg; r.G2 *= sg; r.C0 *= sg; r.C1 *= sg;
+        double gmn, gmx, cmn, cmx;
+        record_ranges(r, t0, t1, gmn, gmx, cmn, cmx);
+        maxg = fmax(maxg, gmx);
+        if (j >= 1 && j <= N - 2) {
+            const double Fmin = gmn * r.R, Fmax = gmx * r.R;
+            U = fmax(U, cmx >= 0.0 ? cmx / Fmin : cmx / Fmax);
+            minC = fmin(minC, cmn); minF = fmin(minF, Fmin); maxF = fmax(maxF, Fmax);
+        }
+        int off = 0;
+        for (int lev = 0; lev <= nlev; ++lev) {
+            if (j & ((1 << lev) - 1)) break;
+            const double f4 = (double)(1 << (2 * lev));
+            double2* o = reinterpret_cast<double2*>(out + ((size_t)off + (j >> lev)) * REC);
+            o[0] = make_double2(r.G0, r.G1);
+            o[1] = make_double2(r.G2, r.C0 * f4);
+            o[2] = make_double2(r.C1 * f4, r.R * f4);
+            off += level_n(N, lev);
+        }
+    }
+    U = block_reduce(U, PMax(), scratch);
+    minC = block_reduce(minC, PMin(), scratch);
+    maxg = block_reduce(maxg, PMax(), scratch);
+    minF = block_reduce(minF, PMin(), scratch);
+    maxF = block_reduce(maxF, PMax(), scratch);
+    if (tid == 0) {
+        U = U + 1e-12 * fabs(U) + 1e-300;
+        const double numer = minC - 8.0 * maxg;
+        bounds[2 * line + 0] = U;
+        bounds[2 * line + 1] = 1.000001 * ((numer < 0.0) ? numer / minF : numer / maxF) - 1e-300;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+bool scan_solver_eligible(const SolveParams& p) {
+    if (const char* e = std::getenv("IBS_SCAN")) { if (std::atoi(e) == 0) return false; }
+    if (p.line_of_solve || p.lam0 || p.g_out || p.c_out || p.f_out) return false;
+    if (p.nth0 < 4 || (p.nsolve % p.nth0) != 0) return false;
+    if ((p.N & 1) == 0 || p.N < 65) return false;          // composite Simpson by parity; matching-row margins
+    return true;
+}
+
+template <int SPL>
+static int scan_launch(const ScanParams& sp, cudaStream_t stream) {
+    auto kern = scan_solve_kernel<SPL>;
+    const size_t smem = (size_t)SC_WARPS * SC_RING * sizeof(double) + (size_t)SC_WARPS * SC_NSTAGE * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        IBS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IBS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured = true;
+    }
+    int per_sm = 0;
+    IBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SC_WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (const char* e = std::getenv("IBS_MAX_CTAS_PER_SM")) { const int v = std::atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
+    const long long cap = (long long)num_sms() * per_sm;
+    const long long need = ((long long)sp.nitems + SC_WARPS - 1) / SC_WARPS;
+    const int grid = (int)(need < cap ? need : cap);
+    kern<<<grid, SC_WARPS * 32, smem, stream>>>(sp);
+    IBS_CUDA_CHECK(cudaGetLastError());
+    return IBS_OK;
+}
+
+int scan_solve_dispatch(const SolveParams& p, cudaStream_t stream) {
+    const int N = p.N;
+    const int nline = p.nsolve / p.nth0;
+    const int nlev = num_levels(N);
+    const int rows_total = level_offset(N, nlev + 1);
+    int spl = (p.nth0 > 32) ? 2 : 1;
+    if (const char* e = std::getenv("IBS_SCAN_SPL")) { const int v = std::atoi(e); if (v == 1 || v == 2) spl = v; }
+    keep_pool_cached();
+    const size_t poly_bytes = (size_t)nline * rows_total * REC * sizeof(double);
+    const size_t bounds_off = (poly_bytes + 255) & ~(size_t)255;
+    const size_t counter_off = bounds_off + (((size_t)nline * 2 * sizeof(double) + 255) & ~(size_t)255);
+    const size_t xs_off = counter_off + 256;
+    const size_t xs_bytes = (p.dX_out && !p.X_out) ? (size_t)p.nsolve * N * sizeof(double) : 0;      // X is the scratch dX is formed from
+    char* ws = nullptr;
+    IBS_CUDA_CHECK(cudaMallocAsync((void**)&ws, xs_off + xs_bytes + 256, stream));
+    int rc = IBS_OK;
+    ScanParams sp;
+    sp.poly = (double*)ws; sp.bounds = (double*)(ws + bounds_off); sp.counter = (unsigned*)(ws + counter_off);
+    sp.theta0 = p.theta0; sp.sigma = p.sigma;
+    sp.nline = nline; sp.nth0 = p.nth0; sp.N = N; sp.nlev = nlev; sp.rows_total = rows_total;
+    sp.groups = (p.nth0 + 32 * spl - 1) / (32 * spl);
+    sp.nitems = nline * sp.groups;
+    sp.h = p.h;
+    sp.lam_out = p.lam_out; sp.lam_matrix_out = p.lam_matrix_out; sp.X_out = p.X_out; sp.dX_out = p.dX_out; sp.info_out = p.info_out;
+    sp.X_rows = p.X_out ? p.X_out : (xs_bytes ? (double*)(ws + xs_off) : nullptr);
+    if (cudaMemsetAsync(sp.counter, 0, sizeof(unsigned), stream) != cudaSuccess) rc = IBS_ERR_CUDA;
+    if (rc == IBS_OK) {
+        scan_prep_kernel<<<nline, PREP_T, 0, stream>>>(p.base, p.dPdrho, p.theta0, p.nth0, N, p.h * p.h, nlev, rows_total,
+                                                       (double*)ws, (double*)(ws + bounds_off));
+        if (cudaGetLastError() != cudaSuccess) { set_error("scan_prep_kernel launch failed"); rc = IBS_ERR_CUDA; }
+    }
+    if (rc == IBS_OK) rc = (spl == 2) ? scan_launch<2>(sp, stream) : scan_launch<1>(sp, stream);
+    cudaFreeAsync(ws, stream);
+    return rc;
+}
+
+}  // namespace ibs

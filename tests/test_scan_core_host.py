@@ -1,0 +1,67 @@
+"""CPU check of the lane code of the scan solver (csrc/ibs_scan_core.cuh) through the g++ harness
+tools/scan_core_host.cpp: the same per-lane arithmetic the CUDA kernel runs (division-free twisted recurrences,
+multigrid start, streaming output passes) against the oracle.  The harness is test infrastructure, not a fallback."""
+import os
+import shutil
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import LAM_RTOL, X_ATOL
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    import scan_host_check as shc
+    return shc, shc.build(str(tmp_path_factory.mktemp("sch")))
+
+
+@pytest.mark.parametrize("name,nth0", [("synthetic_d3d", 5), ("synthetic_ncsx", 3), ("synthetic_hberg", 2)])
+def test_lane_code_matches_oracle(harness, golden, name, nth0):
+    shc, lib = harness
+    D = golden(name)
+    ns, na = D["geo_bmag"].shape[:2]
+    base = np.stack([D["geo_" + n] for n in shc.BASE_NAMES], axis=2).reshape(ns * na, 8, -1)
+    th0 = np.tile(np.linspace(0.0, np.pi / 2, nth0), (ns * na, 1))
+    theta = D["theta"]
+    R = shc.host_scan_solve(lib, base, D["dPdrho"].reshape(-1), th0, theta[1] - theta[0], sigma=np.full(th0.size, 1.0))
+    assert np.all((R["info"] >> 16) == 0)
+    assert R["cost"] / th0.size < 12.0                    # fine-grid-equivalent passes per solve (multigrid start)
+    for line in range(ns * na):
+        i, j = divmod(line, na)
+        for t in range(nth0):
+            gam, X, dX, _ = shc.oracle_solve(D, i, j, th0[line, t])
+            s = line * nth0 + t
+            assert abs(R["lam"][line, t] - gam) <= LAM_RTOL * abs(gam)
+            np.testing.assert_allclose(R["X"][s], X, rtol=0, atol=X_ATOL)
+            np.testing.assert_allclose(R["dX"][s], dX, rtol=0, atol=10 * X_ATOL * max(1.0, np.max(np.abs(dX))))
+
+
+def test_lane_code_fixture_values(harness, golden):
+    """Against the stored converged-reference values (ARPACK tol=0 run of the reference itself)."""
+    shc, lib = harness
+    D = golden("synthetic_d3d")
+    ns, na, nt = D["lam_conv"].shape
+    base = np.stack([D["geo_" + n] for n in shc.BASE_NAMES], axis=2).reshape(ns * na, 8, -1)
+    th0 = np.tile(D["theta0s"], (ns * na, 1))
+    theta = D["theta"]
+    R = shc.host_scan_solve(lib, base, D["dPdrho"].reshape(-1), th0, theta[1] - theta[0])
+    np.testing.assert_allclose(R["lam"].reshape(-1), D["lam_conv"].reshape(-1), rtol=LAM_RTOL, atol=0)
+
+
+def test_lane_code_flags_bad_input(harness, golden):
+    shc, lib = harness
+    D = golden("synthetic_d3d")
+    base = np.stack([D["geo_" + n] for n in shc.BASE_NAMES], axis=2).reshape(-1, 8, len(D["theta"]))[:2].copy()
+    base[1, 4, 100] = np.nan                               # gds2 of line 1
+    th0 = np.tile(np.linspace(0.0, 1.0, 3), (2, 1))
+    theta = D["theta"]
+    R = shc.host_scan_solve(lib, base, D["dPdrho"].reshape(-1)[:2], th0, theta[1] - theta[0])
+    assert np.all((R["info"][0] >> 16) == 0) and np.all(np.isfinite(R["lam"][0]))
+    assert np.all((R["info"][1] >> 16) == 2) and np.all(np.isnan(R["lam"][1]))
+    assert np.all(R["X"][3:] == 0.0)

@@ -1,0 +1,111 @@
+"""GPU parity of the lane-per-solve scan kernel (ibs_scan_solver.cu) -- through the C ABI -- against the oracle,
+the stored converged-reference values and the team-per-solve kernel (IBS_SCAN=0)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import LAM_RTOL, X_ATOL, fixture_base, sign_normalise
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve(base, dP, th0, h, nth0, scan, spl=None, **kw):
+    from ideal_ballooning_solver_b200 import engine
+    old = {k: os.environ.get(k) for k in ("IBS_SCAN", "IBS_SCAN_SPL")}
+    os.environ["IBS_SCAN"] = "1" if scan else "0"
+    if spl:
+        os.environ["IBS_SCAN_SPL"] = str(spl)
+    try:
+        return engine.solve_base_batch(base, dP, th0, h, nth0=nth0, **kw)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("name", ["synthetic_d3d", "synthetic_ncsx", "synthetic_hberg", "ncsx_wout_op"])
+@pytest.mark.parametrize("nth0,spl", [(5, 1), (37, 1), (70, 2), (64, 2)])
+def test_scan_kernel_matches_team_kernel_and_oracle(cuda_lib, golden, name, nth0, spl):
+    import torch
+    from ideal_ballooning_solver_b200 import engine
+    from oracle import ballooning_oracle as bo
+    D = golden(name)
+    theta = D["theta"]
+    if (len(theta) & 1) == 0 or len(theta) < 65:
+        pytest.skip("scan kernel needs an odd number of points")
+    h = engine.grid_spacing(theta)
+    fb = fixture_base(D)
+    ns, na = fb.shape[:2]
+    base = torch.from_numpy(fb).cuda()
+    dP = torch.from_numpy(D["dPdrho"]).cuda()
+    t0 = np.linspace(0.0, np.pi / 2, nth0)
+    th0 = torch.from_numpy(np.tile(t0, ns * na)).cuda()
+    sigma = torch.full((th0.numel(),), 1.0, dtype=torch.float64)
+    new = _solve(base, dP, th0, h, nth0, True, spl, sigma=sigma)
+    old = _solve(base, dP, th0, h, nth0, False, sigma=sigma)
+    assert np.all(new.flags.cpu().numpy() == old.flags.cpu().numpy())
+    lam_n, lam_o = new.lam.cpu().numpy(), old.lam.cpu().numpy()
+    np.testing.assert_allclose(lam_n, lam_o, rtol=LAM_RTOL, atol=0)
+    assert np.array_equal(lam_n > 0, lam_o > 0)
+    np.testing.assert_allclose(new.lam_matrix.cpu().numpy(), old.lam_matrix.cpu().numpy(), rtol=LAM_RTOL, atol=0)
+    Xn, Xo = new.X.cpu().numpy(), old.X.cpu().numpy()
+    np.testing.assert_allclose(Xn, Xo, rtol=0, atol=X_ATOL)
+    assert np.all(Xn.max(axis=1) == 1.0) and np.all(Xn[:, 0] == 0) and np.all(Xn[:, -1] == 0)
+    dXn, dXo = new.dX.cpu().numpy(), old.dX.cpu().numpy()
+    np.testing.assert_allclose(dXn, dXo, rtol=0, atol=10 * X_ATOL * max(1.0, np.abs(dXo).max()))
+    assert new.iterations.max().item() < 64
+    # a sample against the oracle (LAPACK on the same pencil + the reference's post-processing)
+    rng = np.random.default_rng(7)
+    for s in rng.choice(th0.numel(), size=4, replace=False):
+        line, t = divmod(int(s), nth0)
+        i, j = divmod(line, na)
+        cv = D["geo_cvdrift"][i, j] + t0[t] * D["geo_cvdrift0"][i, j]
+        gd = D["geo_gds2"][i, j] + 2 * t0[t] * D["geo_gds21"][i, j] + t0[t] ** 2 * D["geo_gds22"][i, j]
+        gam, X, dX, *_ = bo.gamma_ball_full(D["dPdrho"][i, j], theta, D["geo_bmag"][i, j], D["geo_gradpar_theta_pest"][i, j],
+                                            cv, gd, method="lambda_max")
+        assert abs(lam_n[s] - gam) <= LAM_RTOL * abs(gam)
+        np.testing.assert_allclose(Xn[s], sign_normalise(X), rtol=0, atol=X_ATOL)
+
+
+def test_scan_kernel_fixture_values(cuda_lib, golden):
+    """Stored converged-reference eigenvalues (the reference itself, ARPACK tol=0) at the fixture's theta0, padded to a
+    scan-shaped batch."""
+    import torch
+    from ideal_ballooning_solver_b200 import engine
+    D = golden("synthetic_ncsx")
+    theta = D["theta"]
+    h = engine.grid_spacing(theta)
+    fb = fixture_base(D)
+    ns, na = fb.shape[:2]
+    t0 = np.concatenate([D["theta0s"], np.linspace(0.05, 1.5, 6)])
+    nt = len(D["theta0s"])
+    th0 = torch.from_numpy(np.tile(t0, ns * na)).cuda()
+    sol = _solve(torch.from_numpy(fb).cuda(), torch.from_numpy(D["dPdrho"]).cuda(), th0, h, len(t0), True)
+    lam = sol.lam.cpu().numpy().reshape(ns, na, len(t0))[:, :, :nt]
+    np.testing.assert_allclose(lam, D["lam_conv"], rtol=LAM_RTOL, atol=0)
+    X = sol.X.cpu().numpy().reshape(ns, na, len(t0), -1)[:, :, :nt]
+    np.testing.assert_allclose(X, sign_normalise(D["X_conv"]), rtol=0, atol=X_ATOL)
+
+
+def test_scan_kernel_outputs_optional_and_bad_input(cuda_lib, golden):
+    import torch
+    from ideal_ballooning_solver_b200 import engine
+    D = golden("synthetic_d3d")
+    theta = D["theta"]
+    h = engine.grid_spacing(theta)
+    fb = fixture_base(D).reshape(-1, 8, len(theta))[:2].copy()
+    fb[1, 4, 100] = np.nan
+    th0 = torch.from_numpy(np.tile(np.linspace(0, 1.2, 9), 2)).cuda()
+    dP = torch.from_numpy(D["dPdrho"].reshape(-1)[:2].copy()).cuda()
+    base = torch.from_numpy(fb).cuda()
+    full = _solve(base, dP, th0, h, 9, True)
+    lean = _solve(base, dP, th0, h, 9, True, want_X=False, want_dX=False, want_matrix=False)
+    assert torch.equal(full.lam[:9], lean.lam[:9])
+    only_dX = _solve(base, dP, th0, h, 9, True, want_X=False, want_dX=True)          # X is then internal scratch
+    assert torch.equal(only_dX.dX[:9], full.dX[:9]) and torch.all(only_dX.dX[9:] == 0)
+    fl = full.flags.cpu().numpy()
+    assert np.all(fl[:9] == 0) and np.all(fl[9:] == 2)
+    assert torch.isnan(full.lam[9:]).all() and torch.all(full.X[9:] == 0)

@@ -27,6 +27,17 @@ struct HostCtx {
     int min_i(int v) const { return v; }
     int max_i(int v) const { return v; }
     int first_i(int v) const { return v; }
+    void sync_mem() const {}
+    std::vector<double> scr = std::vector<double>(4096);
+    double* scratch() { return scr.data(); }
+    double ld(const double* p) const { return *p; }
+    int ldi(const int* p) const { return *p; }
+    template <int SPL>
+    void fixup(const bool (&wr)[SPL], double* const (&Xrow)[SPL], double* const (&dXrow)[SPL], int N_, const SolveOut (&out)[SPL],
+               double h, bool want_dX) {
+        for (int q = 0; q < SPL; ++q)
+            if (wr[q]) fixup_solve(*this, Xrow[q], want_dX ? dXrow[q] : nullptr, N_, out[q].bad, h, 0, 1);
+    }
 };
 }  // namespace
 
@@ -94,7 +105,8 @@ extern "C" long scan_host_solve(const double* poly, const double* bounds, const 
             const double th0[1] = {theta0[s]};
             const bool act[1] = {true};
             const double sg[1] = {sigma ? sigma[s] : 0.0};
-            double* const Xrow[1] = {X_out ? X_out + s * N : nullptr};
+            std::vector<double> xscratch(N);
+            double* const Xrow[1] = {X_out ? X_out + s * N : xscratch.data()};
             double* const dXrow[1] = {dX_out ? dX_out + s * N : nullptr};
             ItemResult res[1];
             solve_item<1>(ctx, P, th0, act, sg, sigma != nullptr, Xrow, dXrow, res);
