@@ -836,7 +836,7 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
             bool alldone = true;
 #pragma unroll
             for (int q = 0; q < SPL; ++q) {
-                if (!it[q].done) ++nev[q];
+                if (!it[q].done) nev[q] += 8 >> lev;         // in eighths of a fine-grid evaluation (MAXLEV = 3)
                 iter_update(it[q], r[q], S[q], nodes[q], P.U, tol, tol_stag, (lev > 0) ? 1e-7 * scale : tol, lev == 0);
                 alldone &= it[q].done;
                 sh[q] = it[q].lam;
@@ -943,7 +943,8 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
     }
 #pragma unroll
     for (int q = 0; q < SPL; ++q) {
-        const int itc = (flags[q] & FLAG_BAD_INPUT) ? 0 : ((flags[q] & FLAG_NOT_CONVERGED) ? 64 : imin(nev[q], 0xffff));
+        // iterations reported = fine-grid-equivalent evaluations of the iteration (coarse levels count by their size)
+        const int itc = (flags[q] & FLAG_BAD_INPUT) ? 0 : ((flags[q] & FLAG_NOT_CONVERGED) ? 64 : imin((nev[q] + 7) / 8, 63));
         res[q].info = itc | (flags[q] << 16);
     }
 }

@@ -290,7 +290,7 @@ int scan_solve_dispatch(const SolveParams& p, cudaStream_t stream) {
     const int nline = p.nsolve / p.nth0;
     const int nlev = num_levels(N);
     const int rows_total = level_offset(N, nlev + 1);
-    int spl = (p.nth0 > 32) ? 2 : 1;
+    int spl = 1;        // two solves per lane (IBS_SCAN_SPL=2) halve the shared-memory traffic but spill at 255 registers: slower
     if (const char* e = std::getenv("IBS_SCAN_SPL")) { const int v = std::atoi(e); if (v == 1 || v == 2) spl = v; }
     keep_pool_cached();
     const size_t poly_bytes = (size_t)nline * rows_total * REC * sizeof(double);
