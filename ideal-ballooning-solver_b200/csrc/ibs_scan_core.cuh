@@ -26,13 +26,20 @@
 #else
 #define IBS_HD inline
 #endif
+// The streaming passes: optionally compiled as real functions (IBS_SCAN_NOINLINE), so that the caller's cold state is
+// saved once at the call instead of competing for registers with the pass's loops.
+#if defined(__CUDACC__) && defined(IBS_SCAN_NOINLINE)
+#define IBS_PASS __host__ __device__ __noinline__
+#else
+#define IBS_PASS IBS_HD
+#endif
 
 namespace ibs {
 namespace scan {
 
 constexpr int TR = 32;            // records per tile (one pipeline stage holds one forward and one backward tile)
 constexpr int REC = 6;            // doubles per record: G0 G1 G2 (g = G0 + th0 G1 + th0^2 G2), C0 C1 (2 h^2 c), R (2 h^2 f = g R)
-constexpr int MAXLEV = 3;         // coarse levels (strides 2, 4, 8)
+constexpr int MAXLEV = 4;         // coarse levels (strides 2, 4, 8, 16)
 constexpr int MIN_COARSE_N = 65;  // a level is used only if it has at least this many points
 constexpr int MAXIT_LEVEL = 64;   // evaluations per level before giving up
 constexpr int K_MARGIN = 8;       // matching row kept this far from both ends
@@ -231,99 +238,141 @@ IBS_HD void joint_step(const Rec& nf, const Rec& nb, double th0, double lam, Co&
 // One evaluation at the shifts lam[]: twisted residual r' (= 2 r), S' = sum 2F z^2 (z_k = 1), node count.
 // rho = lam + r' / S' is the Rayleigh quotient of z; #eigenvalues above lam = nodes + (r' > 0).
 template <int SPL, class Ctx>
-IBS_HD void eval_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL], const double (&lam)[SPL],
+IBS_PASS void eval_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL], const double (&lam)[SPL],
                       double (&r)[SPL], double (&S)[SPL], int (&nodes)[SPL]) {
     const int qf_end = k, qb_end = Nl - 1 - k;           // last record of each direction (row k)
     const int qmin = imin(qf_end, qb_end), qmax = imax(qf_end, qb_end);
     const int nst = qmax / TR + 1;
+    const int nfs = qmin / TR;                            // stages whose 32 steps are interior in both directions
     ctx.begin_pass(lev, Nl, k, nst);
     double Xf[SPL], Wf[SPL], Sf[SPL], gf[SPL], Xb[SPL], Wb[SPL], Sb[SPL], gb[SPL], tb[SPL];
 #pragma unroll
     for (int q = 0; q < SPL; ++q) nodes[q] = 0;
-    for (int s = 0; s < nst; ++s) {
-        ctx.wait(s);
-        int i0 = 0;
-        if (s == 0) {
-            const Rec f0 = load_rec(ctx.frec(0)), f1 = load_rec(ctx.frec(1));
-            const Rec b0 = load_rec(ctx.brec(0)), b1 = load_rec(ctx.brec(1));
+    // ---- stage 0: records 0 and 1 of both directions start the chains
+    ctx.wait(0);
+    {
+        const Rec f0 = load_rec(ctx.frec(0)), f1 = load_rec(ctx.frec(1));
+        const Rec b0 = load_rec(ctx.brec(0)), b1 = load_rec(ctx.brec(1));
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) {
+            double g, C, F;
+            coef(f0, th0[q], g, C, F);
+            gf[q] = g; Xf[q] = 0.0; Wf[q] = 1.0; Sf[q] = 0.0;
+            fwd_step(f1, th0[q], lam[q], Xf[q], Wf[q], Sf[q], gf[q]);           // row 1: X_1 = 1 > 0
+            coef(b0, th0[q], g, C, F);
+            const double gN = g;
+            coef(b1, th0[q], g, C, F);                                          // row M = Nl - 2
+            gb[q] = g; Xb[q] = 1.0; Wb[q] = -(g + gN); Sb[q] = F; tb[q] = fma(-lam[q], F, C);
+        }
+    }
+    int s_next = 0;          // first stage the general loop below has to handle (stage 0 from step 2 if there is no fast region)
+    int i_first = 2;
+    if (nfs > 0) {
+        // ---- fast region: steps 2 .. 32 nfs - 1, ONE software pipeline across the stage boundaries (records two steps
+        // ahead through running pointers, coefficients one step ahead); waits / releases happen inside the loop
+        const int gend = TR * nfs;
+        Co cf[SPL], cb[SPL];
+        unsigned mf[SPL], mb[SPL], ef[SPL], eb[SPL];
+        int hn = 0;                                       // steps in the sign histories
+        const double* pf = ctx.frec(2);
+        const double* pb = ctx.brec(2);
+        {
+            const Rec f = load_rec(pf), b = load_rec(pb);
 #pragma unroll
             for (int q = 0; q < SPL; ++q) {
-                double g, C, F;
-                coef(f0, th0[q], g, C, F);
-                gf[q] = g; Xf[q] = 0.0; Wf[q] = 1.0; Sf[q] = 0.0;
-                fwd_step(f1, th0[q], lam[q], Xf[q], Wf[q], Sf[q], gf[q]);           // row 1: X_1 = 1 > 0
-                coef(b0, th0[q], g, C, F);
-                const double gN = g;
-                coef(b1, th0[q], g, C, F);                                          // row M = Nl - 2
-                gb[q] = g; Xb[q] = 1.0; Wb[q] = -(g + gN); Sb[q] = F; tb[q] = fma(-lam[q], F, C);
+                coef_next(f, th0[q], lam[q], gf[q], cf[q]);
+                coef_next(b, th0[q], lam[q], gb[q], cb[q]);
+                mf[q] = 0; mb[q] = 0; ef[q] = sign_bit(Xf[q]); eb[q] = sign_bit(Xb[q]);
             }
-            i0 = 2;
         }
-        if (TR * s + TR - 1 < qmin) {
-            // fast path (pipelined): the rest of the tile in both directions, no per-step tests; node counts from sign histories
-            Co cf[SPL], cb[SPL];
-            unsigned mf[SPL], mb[SPL], ef[SPL], eb[SPL];
-            {
-                const Rec f = load_rec(ctx.frec(i0)), b = load_rec(ctx.brec(i0));
+        pf += REC; pb -= REC;
+        Rec rf = load_rec(pf), rb = load_rec(pb);         // records of step 3
+        pf += REC; pb -= REC;
+        auto flush = [&](int g_done) {                    // after step g_done (g_done % 16 == 15)
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) { rescale3(Xf[q], Wf[q], Sf[q]); rescale3(Xb[q], Wb[q], Sb[q]); }
+            if ((g_done & (TR - 1)) == TR - 1) {
 #pragma unroll
                 for (int q = 0; q < SPL; ++q) {
-                    coef_next(f, th0[q], lam[q], gf[q], cf[q]);
-                    coef_next(b, th0[q], lam[q], gb[q], cb[q]);
+                    nodes[q] += sign_changes_n(mf[q], hn, ef[q]) + sign_changes_n(mb[q], hn, eb[q]);
                     mf[q] = 0; mb[q] = 0; ef[q] = sign_bit(Xf[q]); eb[q] = sign_bit(Xb[q]);
                 }
+                hn = 0;
+                ctx.release(g_done / TR);                 // every record of that stage has been consumed
             }
-            Rec rf = load_rec(ctx.frec(i0 + 1)), rb = load_rec(ctx.brec(i0 + 1));
-#pragma unroll 2
-            for (int i = i0; i < TR - 1; ++i) {
-                const Rec nf = load_rec(ctx.frec(i + 2)), nb = load_rec(ctx.brec(i + 2));      // (slot 32 of the last step: unused)
-#pragma unroll
-                for (int q = 0; q < SPL; ++q) {
-                    joint_step(rf, rb, th0[q], lam[q], cf[q], cb[q], gf[q], gb[q], Xf[q], Wf[q], Sf[q], Xb[q], Wb[q], Sb[q], tb[q]);
-                    mf[q] = (mf[q] << 1) | sign_bit(Xf[q]);
-                    mb[q] = (mb[q] << 1) | sign_bit(Xb[q]);
-                }
-                if ((i & 15) == 15) {
-#pragma unroll
-                    for (int q = 0; q < SPL; ++q) { rescale3(Xf[q], Wf[q], Sf[q]); rescale3(Xb[q], Wb[q], Sb[q]); }
-                }
-                rf = nf; rb = nb;
+        };
+        int g = 2;
+#pragma unroll 1
+        for (; g + 3 < gend; g += 2) {
+            // step g (even): the records of step g + 2 may be the first ones of the next stage
+            if (((g + 2) & (TR - 1)) == 0) {
+                ctx.wait((g + 2) / TR);
+                pf = ctx.frec(0); pb = ctx.brec(0);
             }
+            const Rec nf = load_rec(pf), nb = load_rec(pb);
+            pf += REC; pb -= REC;
 #pragma unroll
-            for (int q = 0; q < SPL; ++q) {          // last step of the tile: its coefficients are ready
-                fwd_chain(cf[q], Xf[q], Wf[q], Sf[q]);
-                bwd_chain(cb[q], Xb[q], Wb[q], Sb[q], tb[q]);
+            for (int q = 0; q < SPL; ++q) {
+                joint_step(rf, rb, th0[q], lam[q], cf[q], cb[q], gf[q], gb[q], Xf[q], Wf[q], Sf[q], Xb[q], Wb[q], Sb[q], tb[q]);
                 mf[q] = (mf[q] << 1) | sign_bit(Xf[q]);
                 mb[q] = (mb[q] << 1) | sign_bit(Xb[q]);
-                rescale3(Xf[q], Wf[q], Sf[q]); rescale3(Xb[q], Wb[q], Sb[q]);
-                nodes[q] += sign_changes_n(mf[q], TR - i0, ef[q]) + sign_changes_n(mb[q], TR - i0, eb[q]);
             }
-        } else {
+            // step g + 1 (odd)
+            rf = load_rec(pf); rb = load_rec(pb);
+            pf += REC; pb -= REC;
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) {
+                joint_step(nf, nb, th0[q], lam[q], cf[q], cb[q], gf[q], gb[q], Xf[q], Wf[q], Sf[q], Xb[q], Wb[q], Sb[q], tb[q]);
+                mf[q] = (mf[q] << 1) | sign_bit(Xf[q]);
+                mb[q] = (mb[q] << 1) | sign_bit(Xb[q]);
+            }
+            hn += 2;
+            if (((g + 1) & 15) == 15) flush(g + 1);
+        }
+        // steps gend - 2 (its successor's coefficients from the record already loaded) and gend - 1 (chains only)
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) {
+            joint_step(rf, rb, th0[q], lam[q], cf[q], cb[q], gf[q], gb[q], Xf[q], Wf[q], Sf[q], Xb[q], Wb[q], Sb[q], tb[q]);
+            mf[q] = (mf[q] << 1) | sign_bit(Xf[q]);
+            mb[q] = (mb[q] << 1) | sign_bit(Xb[q]);
+            fwd_chain(cf[q], Xf[q], Wf[q], Sf[q]);
+            bwd_chain(cb[q], Xb[q], Wb[q], Sb[q], tb[q]);
+            mf[q] = (mf[q] << 1) | sign_bit(Xf[q]);
+            mb[q] = (mb[q] << 1) | sign_bit(Xb[q]);
+        }
+        hn += 2;
+        flush(gend - 1);
+        s_next = nfs;
+        i_first = 0;
+    }
+    // ---- general steps (the ends of the chains, unequal chains): one step at a time with per-step tests
+    for (int s = s_next; s < nst; ++s) {
+        if (s > 0 || nfs > 0) ctx.wait(s);
 #pragma unroll 1
-            for (int i = i0; i < TR && TR * s + i <= qmax; ++i) {
-                const int qq = TR * s + i;
-                if (qq <= qf_end) {
-                    const Rec rf = load_rec(ctx.frec(i));
+        for (int i = (s == s_next) ? i_first : 0; i < TR && TR * s + i <= qmax; ++i) {
+            const int qq = TR * s + i;
+            if (qq <= qf_end) {
+                const Rec rf = load_rec(ctx.frec(i));
 #pragma unroll
-                    for (int q = 0; q < SPL; ++q) {
-                        const unsigned s0 = sign_bit(Xf[q]);
-                        fwd_step(rf, th0[q], lam[q], Xf[q], Wf[q], Sf[q], gf[q]);
-                        nodes[q] += (int)(s0 ^ sign_bit(Xf[q]));
-                    }
+                for (int q = 0; q < SPL; ++q) {
+                    const unsigned s0 = sign_bit(Xf[q]);
+                    fwd_step(rf, th0[q], lam[q], Xf[q], Wf[q], Sf[q], gf[q]);
+                    nodes[q] += (int)(s0 ^ sign_bit(Xf[q]));
                 }
-                if (qq <= qb_end) {
-                    const Rec rb = load_rec(ctx.brec(i));
+            }
+            if (qq <= qb_end) {
+                const Rec rb = load_rec(ctx.brec(i));
 #pragma unroll
-                    for (int q = 0; q < SPL; ++q) {
-                        const unsigned s0 = sign_bit(Xb[q]);
-                        if (qq < qb_end) bwd_step<true>(rb, th0[q], lam[q], Xb[q], Wb[q], Sb[q], gb[q], tb[q]);
-                        else bwd_step<false>(rb, th0[q], lam[q], Xb[q], Wb[q], Sb[q], gb[q], tb[q]);     // row k: counted by the forward sum
-                        nodes[q] += (int)(s0 ^ sign_bit(Xb[q]));
-                    }
+                for (int q = 0; q < SPL; ++q) {
+                    const unsigned s0 = sign_bit(Xb[q]);
+                    if (qq < qb_end) bwd_step<true>(rb, th0[q], lam[q], Xb[q], Wb[q], Sb[q], gb[q], tb[q]);
+                    else bwd_step<false>(rb, th0[q], lam[q], Xb[q], Wb[q], Sb[q], gb[q], tb[q]);     // row k: counted by the forward sum
+                    nodes[q] += (int)(s0 ^ sign_bit(Xb[q]));
                 }
-                if ((i & 15) == 15) {
+            }
+            if ((i & 15) == 15) {
 #pragma unroll
-                    for (int q = 0; q < SPL; ++q) { rescale3(Xf[q], Wf[q], Sf[q]); rescale3(Xb[q], Wb[q], Sb[q]); }
-                }
+                for (int q = 0; q < SPL; ++q) { rescale3(Xf[q], Wf[q], Sf[q]); rescale3(Xb[q], Wb[q], Sb[q]); }
             }
         }
         ctx.release(s);
@@ -347,6 +396,7 @@ struct Sweep {
     double a0e, a0o, a1e, a1o, aDe, aDo;   // sum t' X^2, sum F' X^2, sum g D^2 of the even / odd rows (no dynamic indexing)
     double aEnd;                  // g D^2 of the Dirichlet end point
     double vmax; int jmax;        // largest |x| so far (running scale) and its row
+    int nodes;                    // sign changes of x along the sweep
     bool bad;
     double fsc, cn; int ex;       // writing pass: X = x * fsc, fsc = cn 2^ex (ex follows the rescalings)
 };
@@ -354,6 +404,7 @@ struct Sweep {
 struct SolveOut {                 // what the output pass returns per solve
     double gam, zmax; int jmax; bool bad;
     double xkf, xkb; int Ekf, Ekb;     // the two sweeps at the matching row: value and scale exponent
+    double r, S; int nodes;            // what eval_pass returns (the pass can stand in for an evaluation)
 };
 
 constexpr double C23 = 2.0 / 3.0, C12 = 1.0 / 12.0;
@@ -396,6 +447,7 @@ IBS_HD void out_step(Sweep& sw, const Rec& rc, double th0, double lam, int qq, i
     double xn;
     if (DIR > 0) { xn = fma(sw.w, ia, sw.x); sw.w = fma(-tnew, xn, sw.w); }
     else         { sw.w = fma(sw.tcur, sw.x, sw.w); xn = fma(-sw.w, ia, sw.x); sw.tcur = tnew; }
+    if (!WRITE) sw.nodes += (int)(sign_bit(sw.x) ^ sign_bit(xn));
     sw.x = xn;
     if (WRITE) {
         if (!last && Xw) Xw[row] = norm_value(xn, sw.fsc);
@@ -428,7 +480,7 @@ IBS_HD void out_step(Sweep& sw, const Rec& rc, double th0, double lam, int qq, i
 IBS_HD void sweep_zero(Sweep& sw) {
     sw.E = 0; sw.W1 = sw.W2 = sw.W3 = sw.W4 = 0.0; sw.tcur = 0.0;
     sw.a0e = sw.a0o = sw.a1e = sw.a1o = sw.aDe = sw.aDo = 0.0; sw.aEnd = 0.0;
-    sw.vmax = 0.0; sw.jmax = 0; sw.bad = false;
+    sw.vmax = 0.0; sw.jmax = 0; sw.nodes = 0; sw.bad = false;
 }
 
 // ---- pipelined form of the output-pass step (interior rows: generic stencil, never the last backward step) -----
@@ -440,6 +492,7 @@ IBS_HD void out_chain_tail(Sweep& sw, const OCo& c, int row, double* Xw) {
     double xn;
     if (DIR > 0) { xn = fma(sw.w, c.ia, sw.x); sw.w = fma(-c.t, xn, sw.w); }
     else         { sw.w = fma(sw.tcur, sw.x, sw.w); xn = fma(-sw.w, c.ia, sw.x); sw.tcur = c.t; }
+    if (!WRITE) sw.nodes += (int)(sign_bit(sw.x) ^ sign_bit(xn));
     sw.x = xn;
     if (WRITE) {
         if (Xw) Xw[row] = norm_value(xn, sw.fsc);
@@ -527,7 +580,7 @@ IBS_HD void out_joint(const Rec& nf, const Rec& nb, double th0, double lam, OCo&
 //   WRITE = true : the chains are recomputed (bit-identically) and X = z / max|z| is written to Xw[q] (where not null),
 //                  using the scales out[] of the first pass
 template <int SPL, bool WRITE, class Ctx>
-IBS_HD void out_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL], const double (&lam)[SPL],
+IBS_PASS void out_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL], const double (&lam)[SPL],
                      SolveOut (&out)[SPL], double* const (&Xw)[SPL]) {
     const int qf_end = k, qb_end = Nl - 1 - k;
     const int qmin = imin(qf_end, qb_end), qmax = imax(qf_end, qb_end);
@@ -664,6 +717,9 @@ IBS_HD void out_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL],
         const double sX0 = zf2 * (w43 * f.a0o + w23 * f.a0e) + zb2 * (w43 * b.a0o + w23 * b.a0e);
         const double sX1 = zf2 * (w43 * f.a1o + w23 * f.a1e) + zb2 * (w43 * b.a1o + w23 * b.a1e);
         o.gam = lam[q] + (sX0 - 2.0 * sD) / sX1;
+        o.r = b.w * zb - f.w * zf;
+        o.S = zf2 * (f.a1o + f.a1e) + zb2 * (b.a1o + b.a1e);
+        o.nodes = f.nodes + b.nodes;
         const double mf = f.vmax * fabs(zf), mb = b.vmax * fabs(zb);
         o.zmax = fmax(mf, mb);
         o.jmax = (mb > mf) ? b.jmax : f.jmax;
@@ -796,7 +852,7 @@ struct ItemResult { double gam, rho; int info; };
 //          with the matching row moved to their peak (at most three times) before they are accepted
 //          then X (stored raw by O1) is normalised and dX formed by the context's fix-up (coalesced over the rows)
 //   SIGMA  one count at 2 sigma - lambda (utils.py:1597 returns the eigenvalue nearest sigma; the engine lambda_max)
-enum { PH_ITER = 0, PH_PEAK = 1, PH_O1 = 2, PH_SIGMA = 4 };
+enum { PH_ITER = 0, PH_PEAK = 1, PH_O1 = 2, PH_O2 = 3, PH_SIGMA = 4 };
 
 template <int SPL, class Ctx>
 IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL], const bool (&act)[SPL], const double (&sigma)[SPL],
@@ -809,14 +865,16 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
     Iter it[SPL];
     double sh[SPL], r[SPL], S[SPL], rho1[SPL], rho2[SPL];     // sh: the shifts of the next pass
     int nodes[SPL], nev[SPL], flags[SPL];
-    bool fin[SPL], wr[SPL], need[SPL];
+    bool fin[SPL], wr[SPL], need[SPL], o1at[SPL];      // o1at: the solve's last iteration pass was an output pass
+    double rbest[SPL];                                  // best eigenvalue estimate of the matrix pencil
+    bool skip_o1 = false;
     SolveOut out[SPL];
     double* Xraw[SPL];
     const bool want_out = P.want_X || P.want_dX;
 #pragma unroll
     for (int q = 0; q < SPL; ++q) {
         Xraw[q] = nullptr;
-        rho1[q] = qnan; rho2[q] = qnan; nev[q] = 0; flags[q] = 0; fin[q] = false; wr[q] = false; need[q] = false;
+        rho1[q] = qnan; rho2[q] = qnan; nev[q] = 0; flags[q] = 0; fin[q] = false; wr[q] = false; need[q] = false; o1at[q] = false; rbest[q] = qnan;
         res[q].gam = qnan; res[q].rho = qnan;
         iter_init(it[q], qnan, P.Lb, P.U, false);
         sh[q] = it[q].lam;
@@ -824,9 +882,30 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
     int lev = P.nlev, Nl = level_n(N, lev), k = clamp_k((Nl - 1) / 2, Nl), round = 0, phase = PH_ITER;
     bool lowq_any = false;
     int jsel = -1;
+    bool fix_any = false;
     for (;;) {
+        // ---- the streaming pass of this phase: ONE call site per kind of pass
+        // Fine level, once the corrections are small: the output pass stands in for the evaluation (same chains with
+        // reciprocals; it also returns r, S and the node count), so that the pass that confirms convergence is the one
+        // that delivers the eigenfunction sums.
+        bool o1it = false;
+        if (phase == PH_ITER && lev == 0) {
+            bool near = true;
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) near = near && (it[q].done || it[q].dprev <= 1e-4 * scale);
+            o1it = ctx.all(near);
+        }
+        const int kind = (phase == PH_ITER) ? (o1it ? 2 : 1) : (phase == PH_SIGMA) ? 1 : (phase == PH_PEAK) ? 2 :
+                         (phase == PH_O1) ? (skip_o1 ? 0 : 2) : 3;
+        if (kind == 1) eval_pass<SPL>(ctx, lev, Nl, k, th0, sh, r, S, nodes);
+        else if (kind == 2) out_pass<SPL, false>(ctx, lev, Nl, k, th0, sh, out, Xraw);
+        else if (kind == 3) out_pass<SPL, true>(ctx, lev, Nl, k, th0, sh, out, Xraw);
+        // ---- what the phase does with it
         if (phase == PH_ITER || phase == PH_SIGMA) {
-            eval_pass<SPL>(ctx, lev, Nl, k, th0, sh, r, S, nodes);
+            if (o1it) {
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) { r[q] = out[q].r; S[q] = out[q].S; nodes[q] = out[q].nodes; }
+            }
             if (phase == PH_SIGMA) {
 #pragma unroll
                 for (int q = 0; q < SPL; ++q)
@@ -836,7 +915,10 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
             bool alldone = true;
 #pragma unroll
             for (int q = 0; q < SPL; ++q) {
-                if (!it[q].done) nev[q] += 8 >> lev;         // in eighths of a fine-grid evaluation (MAXLEV = 3)
+                if (!it[q].done) {
+                    nev[q] += (1 << MAXLEV) >> lev;     // in units of the coarsest level's share of a fine-grid evaluation
+                    o1at[q] = o1it;
+                }
                 iter_update(it[q], r[q], S[q], nodes[q], P.U, tol, tol_stag, (lev > 0) ? 1e-7 * scale : tol, lev == 0);
                 alldone &= it[q].done;
                 sh[q] = it[q].lam;
@@ -853,19 +935,27 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
                     continue;
                 }
             } else {
+                // the eigenfunction sums of the last pass can be kept if that pass was an output pass of this very solve
+                // at a shift already within ~1e-10 (relative to the gap) of the eigenvalue: its correction contracted by
+                // 1e-5 or is at the rounding floor
+                bool keep = true;
 #pragma unroll
                 for (int q = 0; q < SPL; ++q)
                     if (!fin[q]) {
-                        sh[q] = (it[q].conv && it[q].rho == it[q].rho) ? it[q].rho : it[q].lam;
+                        const bool good = it[q].conv && it[q].rho == it[q].rho;
+                        rbest[q] = good ? it[q].rho : it[q].lam;
+                        const bool ok1 = o1at[q] && good && (it[q].dprev <= tol || it[q].dprev <= 1e-5 * it[q].dprev2);
+                        sh[q] = ok1 ? it[q].lam : rbest[q];            // (it.lam = the shift of the last pass)
+                        keep = keep && ok1;
                         if (!it[q].conv) flags[q] |= FLAG_NOT_CONVERGED;
                     }
+                skip_o1 = ctx.all(keep);
                 phase = PH_O1;
                 continue;
             }
         } else if (phase == PH_PEAK) {
             // matching row from the coarsest eigenfunctions: the middle of the range of the lanes' peaks -- unless that is
             // close to the middle row, which keeps the two chains equally long (everything on the fast path)
-            out_pass<SPL, false>(ctx, lev, Nl, k, th0, sh, out, Xraw);
             int jlo = 1 << 30, jhi = -1;
 #pragma unroll
             for (int q = 0; q < SPL; ++q) { jlo = imin(jlo, out[q].jmax); jhi = imax(jhi, out[q].jmax); }
@@ -873,8 +963,9 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
             const int kp = (jlo + jhi) / 2, km = (Nl - 1) / 2;
             k = clamp_k((kp > km ? kp - km : km - kp) * PEAK_SNAP <= Nl ? km : kp, Nl);
         } else if (phase == PH_O1) {
-            out_pass<SPL, false>(ctx, 0, N, k, th0, sh, out, Xraw);
-            bool wr_any = false, fix_any = false;
+            skip_o1 = false;
+            bool wr_any = false;
+            fix_any = false;
             lowq_any = false; jsel = -1;
 #pragma unroll
             for (int q = 0; q < SPL; ++q) {
@@ -883,7 +974,7 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
                 if (newly) {
                     fin[q] = true;
                     res[q].gam = out[q].bad ? qnan : out[q].gam;
-                    res[q].rho = out[q].bad ? qnan : sh[q];
+                    res[q].rho = out[q].bad ? qnan : rbest[q];
                     if (out[q].bad) flags[q] = FLAG_BAD_INPUT;
                 }
                 if (lowq && jsel < 0) jsel = out[q].jmax;
@@ -897,11 +988,13 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
                 // second pass: X of the solves accepted in this round (invalid ones are zero-filled by the fix-up)
 #pragma unroll
                 for (int q = 0; q < SPL; ++q) Xraw[q] = (wr[q] && !out[q].bad) ? Xrow[q] : nullptr;
-                out_pass<SPL, true>(ctx, 0, N, k, th0, sh, out, Xraw);
-#pragma unroll
-                for (int q = 0; q < SPL; ++q) Xraw[q] = nullptr;
-                if (ctx.any(fix_any)) ctx.template fixup<SPL>(wr, Xrow, dXrow, N, out, P.h, P.want_dX);
+                phase = PH_O2;
+                continue;
             }
+        } else {       // PH_O2
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) Xraw[q] = nullptr;
+            if (ctx.any(fix_any)) ctx.template fixup<SPL>(wr, Xrow, dXrow, N, out, P.h, P.want_dX);
         }
         // ---- what follows a finished level (lev > 0), the peak finder, or the output passes of a round
         if (lev > 0) {
@@ -934,8 +1027,8 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
         bool any_need = false;
 #pragma unroll
         for (int q = 0; q < SPL; ++q) {
-            need[q] = (flags[q] & FLAG_BAD_INPUT) == 0 && sigma[q] < sh[q];
-            if (need[q]) sh[q] = 2.0 * sigma[q] - sh[q];
+            need[q] = (flags[q] & FLAG_BAD_INPUT) == 0 && sigma[q] < rbest[q];
+            if (need[q]) sh[q] = 2.0 * sigma[q] - rbest[q];
             any_need |= need[q];
         }
         if (!ctx.any(any_need)) break;
@@ -944,7 +1037,7 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
 #pragma unroll
     for (int q = 0; q < SPL; ++q) {
         // iterations reported = fine-grid-equivalent evaluations of the iteration (coarse levels count by their size)
-        const int itc = (flags[q] & FLAG_BAD_INPUT) ? 0 : ((flags[q] & FLAG_NOT_CONVERGED) ? 64 : imin((nev[q] + 7) / 8, 63));
+        const int itc = (flags[q] & FLAG_BAD_INPUT) ? 0 : ((flags[q] & FLAG_NOT_CONVERGED) ? 64 : imin((nev[q] + (1 << MAXLEV) - 1) >> MAXLEV, 63));
         res[q].info = itc | (flags[q] << 16);
     }
 }
