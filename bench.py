@@ -40,7 +40,13 @@ WORKLOADS = {
     "ncsx":  ("ncsx",  64,  32,    32,  2048,  4),
     "hberg": ("hberg", 256, 64,    1,   8192,  8),
 }
-KERNELS_PER_STEP = 7        # pack_mn, pack_nyq, geometry, dpdrho, poly_prep, solve, argmax  (profiles/launches_*.csv)
+KERNELS_PER_STEP = 7        # pack_mn, pack_nyq, geometry, dpdrho, scan_prep (or poly_prep), scan_solve (or solve), argmax  (profiles/launches_*.csv)
+
+
+def solver_kernel_name(nth0, N):
+    """Which K2+K3 kernel the library dispatches a scan-shaped batch to (mirrors scan_solver_eligible, ibs_scan_solver.cu)."""
+    scan_ok = os.environ.get("IBS_SCAN", "1") != "0" and nth0 >= 4 and (N & 1) == 1 and N >= 65
+    return "scan_solve_kernel (K2+K3, lane per solve)" if scan_ok else "solve_kernel (K2+K3, team per solve)"
 
 
 def workload_grids(name):
@@ -202,7 +208,7 @@ def describe(workload, equilibria):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="d3d", choices=sorted(WORKLOADS))
@@ -266,6 +272,9 @@ def main():
             timers[3].record()
         return sol, val, idx
 
+    # the clock sampler starts BEFORE the warm-up (nvidia-smi's start-up stalls the device for a few ms) and keeps
+    # sampling through the timed region
+    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         sol, val, idx = step()
         flush.zero_()
@@ -274,7 +283,6 @@ def main():
     nbad = int(np.count_nonzero(flags & 3))
     mean_iters = float((sol.info & 0xFFFF).double().mean().item())
 
-    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -347,14 +355,15 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": describe(args.workload, E), "solves_per_step_per_gpu": nsolve,
                    "field_lines_per_step_per_gpu": nlines, "l2": "flushed between timed steps (256 MB write)",
-                   "eigvec": "X written to HBM for every solve", "mean_solver_iterations": mean_iters,
-                   "theta0_chain": chain,
+                   "eigvec": "X written to HBM for every solve",
+                   "mean_solver_iterations": mean_iters,      # fine-grid-equivalent evaluations per solve (output passes not counted)
+                   "solver": solver_kernel_name(nt, N), "theta0_chain": chain,
                    "bad_solves": nbad},
-        "roofline": {"bound": "hbm", "kernel": "solve_kernel (K2+K3)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": solver_kernel_name(nt, N), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": solve_ms,
                      "share_of_step": float(t_solve.sum() / t_step.sum()),
-                     "note": "FP64-pipe / latency bound, not HBM bound (DESIGN.md section 3): frac is the HBM fraction asked for; traffic = ncu dram bytes per launch"},
+                     "note": "FP64-pipe bound, not HBM bound (DESIGN.md section 3): frac is the HBM fraction asked for; kernel_ms = CUDA-event time of the solve call (coefficient prep + solver kernel); traffic = ncu dram bytes per launch of the solver kernel"},
         "kernel_ms": {"geometry(K1 incl. pack+dPdrho)": float(t_geo.mean()), "solve(K2+K3)": solve_ms,
                       "step": float(t_step.mean())},
         "gpu_launches": KERNELS_PER_STEP * args.steps,

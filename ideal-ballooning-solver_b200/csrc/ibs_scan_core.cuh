@@ -44,6 +44,11 @@ constexpr int MIN_COARSE_N = 65;  // a level is used only if it has at least thi
 constexpr int MAXIT_LEVEL = 64;   // evaluations per level before giving up
 constexpr int K_MARGIN = 8;       // matching row kept this far from both ends
 constexpr double LOWQ = 1.0e3;
+// Letting the output pass stand in for the last fine-level evaluation saves ~1 of ~6 fine-grid passes, but its vector is
+// then taken at a shift that is only ~1e-11 converged and the Simpson Rayleigh quotient (which weighs the far end of
+// the spectrum heavily) moves by up to 6e-11 relative: measured, no speed-up at warp level (the acceptance test has
+// to hold for all 32 lanes) -> off.
+constexpr bool OUT_PASS_AS_EVAL = false;
 constexpr int PEAK_SNAP = 16;      // a coarsest-level peak within Nl / PEAK_SNAP rows of the middle keeps the middle matching row    // max|z| / |z_k| above which the matching row is moved (see solve_item)
 
 constexpr int FLAG_NOT_CONVERGED = 1, FLAG_BAD_INPUT = 2, FLAG_SIGMA_NOT_MAX = 4;   // = IBS_FLAG_* of include/ibs_b200.h
@@ -842,6 +847,19 @@ struct ItemProblem {
 };
 struct ItemResult { double gam, rho; int info; };
 
+// The state of a lane's solves that no streaming loop touches (iteration bookkeeping, results of the output pass).
+// It lives in memory the context provides (CUDA: shared memory, one block per thread with an odd stride in doubles, so
+// that the lanes of a warp hit different banks) instead of competing for registers with the passes' loops.
+template <int SPL>
+struct ColdState {
+    Iter it[SPL];
+    SolveOut out[SPL];
+    double rho1[SPL], rho2[SPL], rbest[SPL], Kest[SPL];
+    int nev[SPL], flags[SPL];
+    bool fin[SPL], wr[SPL], need[SPL], o1at[SPL];
+};
+template <int SPL> struct ColdStride { static constexpr int value = (int)((sizeof(ColdState<SPL>) + 7) / 8) | 1; };     // doubles, odd
+
 // Everything for the SPL solves of one lane.  act[q] = false: the slot duplicates a valid solve and writes nothing.
 // Written as a state machine with ONE call site per kind of pass (iteration / output pass), so that the kernel holds
 // a single copy of each streaming loop (instruction cache).
@@ -856,25 +874,30 @@ enum { PH_ITER = 0, PH_PEAK = 1, PH_O1 = 2, PH_O2 = 3, PH_SIGMA = 4 };
 
 template <int SPL, class Ctx>
 IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL], const bool (&act)[SPL], const double (&sigma)[SPL],
-                       const bool has_sigma, double* const (&Xrow)[SPL], double* const (&dXrow)[SPL], ItemResult (&res)[SPL]) {
+                       const bool has_sigma, double* const (&Xrow)[SPL], double* const (&dXrow)[SPL], ItemResult (&res)[SPL],
+                       ColdState<SPL>& cs) {
     // Xrow[q]: the solve's X row (needed, as scratch, also when only dX is wanted)
     const double scale = fmax(fabs(P.U), 1e-3);
     const double tol = 1.7763568394002505e-15 * scale, tol_stag = 1e-10 * scale;
     const double qnan = NAN;
     const int N = P.N;
-    Iter it[SPL];
-    double sh[SPL], r[SPL], S[SPL], rho1[SPL], rho2[SPL];     // sh: the shifts of the next pass
-    int nodes[SPL], nev[SPL], flags[SPL];
-    bool fin[SPL], wr[SPL], need[SPL], o1at[SPL];      // o1at: the solve's last iteration pass was an output pass
-    double rbest[SPL];                                  // best eigenvalue estimate of the matrix pencil
+    Iter (&it)[SPL] = cs.it;
+    SolveOut (&out)[SPL] = cs.out;
+    double (&rho1)[SPL] = cs.rho1; double (&rho2)[SPL] = cs.rho2;
+    double (&rbest)[SPL] = cs.rbest;                    // best eigenvalue estimate of the matrix pencil
+    double (&Kest)[SPL] = cs.Kest;                      // convergence constant e_{n+1} / e_n^2 seen on the previous level
+    int (&nev)[SPL] = cs.nev; int (&flags)[SPL] = cs.flags;
+    bool (&fin)[SPL] = cs.fin; bool (&wr)[SPL] = cs.wr; bool (&need)[SPL] = cs.need;
+    bool (&o1at)[SPL] = cs.o1at;                        // the solve's last iteration pass was an output pass
+    double sh[SPL], r[SPL], S[SPL];                     // sh: the shifts of the next pass
+    int nodes[SPL];
     bool skip_o1 = false;
-    SolveOut out[SPL];
     double* Xraw[SPL];
     const bool want_out = P.want_X || P.want_dX;
 #pragma unroll
     for (int q = 0; q < SPL; ++q) {
         Xraw[q] = nullptr;
-        rho1[q] = qnan; rho2[q] = qnan; nev[q] = 0; flags[q] = 0; fin[q] = false; wr[q] = false; need[q] = false; o1at[q] = false; rbest[q] = qnan;
+        rho1[q] = qnan; rho2[q] = qnan; nev[q] = 0; flags[q] = 0; fin[q] = false; wr[q] = false; need[q] = false; o1at[q] = false; rbest[q] = qnan; Kest[q] = 1e300;
         res[q].gam = qnan; res[q].rho = qnan;
         iter_init(it[q], qnan, P.Lb, P.U, false);
         sh[q] = it[q].lam;
@@ -889,10 +912,11 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
         // reciprocals; it also returns r, S and the node count), so that the pass that confirms convergence is the one
         // that delivers the eigenfunction sums.
         bool o1it = false;
-        if (phase == PH_ITER && lev == 0) {
+        if (OUT_PASS_AS_EVAL && phase == PH_ITER && lev == 0) {
             bool near = true;
 #pragma unroll
-            for (int q = 0; q < SPL; ++q) near = near && (it[q].done || it[q].dprev <= 1e-4 * scale);
+            for (int q = 0; q < SPL; ++q)      // predicted (correction ratio)^2 = error of the vector at this shift <~ 1e-10
+                near = near && (it[q].done || (it[q].dprev <= 1e-4 * scale && Kest[q] * it[q].dprev <= 1e-5));
             o1it = ctx.all(near);
         }
         const int kind = (phase == PH_ITER) ? (o1it ? 2 : 1) : (phase == PH_SIGMA) ? 1 : (phase == PH_PEAK) ? 2 :
@@ -927,7 +951,11 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
             // ---- this level has converged
             if (lev > 0) {
 #pragma unroll
-                for (int q = 0; q < SPL; ++q) { rho2[q] = rho1[q]; rho1[q] = (it[q].conv && it[q].rho == it[q].rho) ? it[q].rho : qnan; }
+                for (int q = 0; q < SPL; ++q) {
+                    rho2[q] = rho1[q]; rho1[q] = (it[q].conv && it[q].rho == it[q].rho) ? it[q].rho : qnan;
+                    // quadratic convergence e_{n+1} = K e_n^2: K from the last two corrections of this level (if it has two)
+                    Kest[q] = (it[q].dprev2 < 1e299 && it[q].dprev2 > 0.0 && it[q].dprev > tol) ? it[q].dprev / (it[q].dprev2 * it[q].dprev2) : 1e300;
+                }
                 if (lev == P.nlev) {
 #pragma unroll
                     for (int q = 0; q < SPL; ++q) sh[q] = (rho1[q] == rho1[q]) ? rho1[q] : it[q].lam;

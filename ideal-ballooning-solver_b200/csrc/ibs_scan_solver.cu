@@ -18,10 +18,13 @@
 namespace ibs {
 using namespace scan;
 
-constexpr int SC_NSTAGE = 4;                       // pipeline stages per warp
+#ifndef IBS_SCAN_NSTAGE
+#define IBS_SCAN_NSTAGE 3
+#endif
+constexpr int SC_NSTAGE = IBS_SCAN_NSTAGE;         // pipeline stages per warp
 constexpr int SC_TILE = TR * REC;                  // doubles per tile (1536 B)
 constexpr int SC_STAGE = 2 * SC_TILE;              // forward + backward tile
-constexpr int SC_RING = SC_NSTAGE * SC_STAGE;      // doubles per warp (12 KB)
+constexpr int SC_RING = SC_NSTAGE * SC_STAGE;      // doubles per warp (9 KB with 3 stages)
 constexpr int SC_WARPS = 4;                        // warps per CTA (they never synchronise with each other)
 #ifndef IBS_SCAN_CTAS1
 #define IBS_SCAN_CTAS1 2      // CTAs per SM the SPL = 1 kernel is compiled for (register cap 65536 / (128 * CTAS))
@@ -132,6 +135,9 @@ scan_solve_kernel(const ScanParams p) {
     DevCtx ctx;
     ctx.ring = sc_smem + warp * SC_RING;
     ctx.bars = reinterpret_cast<uint64_t*>(sc_smem + SC_WARPS * SC_RING) + warp * SC_NSTAGE;
+    // the thread's block of cold state (odd stride in doubles: conflict-free across the lanes of a warp)
+    ColdState<SPL>& cold = *reinterpret_cast<ColdState<SPL>*>(sc_smem + SC_WARPS * SC_RING + SC_WARPS * SC_NSTAGE +
+                                                            (size_t)threadIdx.x * ColdStride<SPL>::value);
     ctx.parity = 0; ctx.lane = lane; ctx.N = p.N;
     if (lane == 0) {
         for (int s = 0; s < SC_NSTAGE; ++s) mbar_init(&ctx.bars[s], 1);
@@ -164,7 +170,7 @@ scan_solve_kernel(const ScanParams p) {
         P.want_X = p.X_rows != nullptr; P.want_dX = p.dX_out != nullptr;
         ctx.line_base = p.poly + (size_t)line * p.rows_total * REC;
         ItemResult res[SPL];
-        solve_item<SPL>(ctx, P, th0, act, sg, p.sigma != nullptr, Xrow, dXrow, res);
+        solve_item<SPL>(ctx, P, th0, act, sg, p.sigma != nullptr, Xrow, dXrow, res, cold);
 #pragma unroll
         for (int q = 0; q < SPL; ++q)
             if (act[q]) {
@@ -266,7 +272,8 @@ bool scan_solver_eligible(const SolveParams& p) {
 template <int SPL>
 static int scan_launch(const ScanParams& sp, cudaStream_t stream) {
     auto kern = scan_solve_kernel<SPL>;
-    const size_t smem = (size_t)SC_WARPS * SC_RING * sizeof(double) + (size_t)SC_WARPS * SC_NSTAGE * sizeof(uint64_t);
+    const size_t smem = (size_t)SC_WARPS * SC_RING * sizeof(double) + (size_t)SC_WARPS * SC_NSTAGE * sizeof(uint64_t) +
+                        (size_t)SC_WARPS * 32 * ColdStride<SPL>::value * sizeof(double);
     static bool configured = false;
     if (!configured) {
         IBS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -109,7 +109,8 @@ extern "C" long scan_host_solve(const double* poly, const double* bounds, const 
             double* const Xrow[1] = {X_out ? X_out + s * N : xscratch.data()};
             double* const dXrow[1] = {dX_out ? dX_out + s * N : nullptr};
             ItemResult res[1];
-            solve_item<1>(ctx, P, th0, act, sg, sigma != nullptr, Xrow, dXrow, res);
+            ColdState<1> cold;
+            solve_item<1>(ctx, P, th0, act, sg, sigma != nullptr, Xrow, dXrow, res, cold);
             lam_out[s] = res[0].gam;
             if (lam_matrix_out) lam_matrix_out[s] = res[0].rho;
             if (info_out) info_out[s] = res[0].info;
