@@ -37,3 +37,14 @@ def fixture_base(D):
     """(ns, nalpha, 8, nl) base array in the engine's row order from a golden fixture."""
     from ideal_ballooning_solver_b200.engine import BASE_NAMES
     return np.stack([D["geo_" + n] for n in BASE_NAMES], axis=2)
+
+
+def s_alpha_base(shat, alpha, theta):
+    """The s-alpha model (bishop_ball_s-alpha.py) as the eight base arrays of a field line, so that the theta0 dependence
+    is the reference's (ball_scan.py:267-268): g = f = 1 + (shat (theta - theta0) - alpha sin theta)^2,
+    c = alpha (cos theta + (...) sin theta).  Returns (base (8, N) in IBS_BASE_* order, dPdrho)."""
+    L0 = shat * theta - alpha * np.sin(theta)
+    one = np.ones_like(theta)
+    base = np.stack([one, one, np.cos(theta) + L0 * np.sin(theta), -shat * np.sin(theta), 1 + L0 ** 2, -shat * L0,
+                     shat ** 2 * one, one])
+    return base, -alpha

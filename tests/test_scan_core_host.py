@@ -8,7 +8,7 @@ import sys
 import numpy as np
 import pytest
 
-from helpers import LAM_RTOL, X_ATOL
+from helpers import LAM_RTOL, X_ATOL, s_alpha_base
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
 
@@ -65,3 +65,21 @@ def test_lane_code_flags_bad_input(harness, golden):
     assert np.all((R["info"][0] >> 16) == 0) and np.all(np.isfinite(R["lam"][0]))
     assert np.all((R["info"][1] >> 16) == 2) and np.all(np.isnan(R["lam"][1]))
     assert np.all(R["X"][3:] == 0.0)
+
+
+def test_lane_code_off_centre_modes(harness):
+    """s-alpha with theta0 up to 20: the eigenfunction peaks up to 600 rows away from the middle of the line
+    (the matching row has to follow it)."""
+    from oracle import ballooning_oracle as bo
+    shc, lib = harness
+    theta = np.linspace(-10 * np.pi, 10 * np.pi, 2049)
+    th0 = np.linspace(0.0, 20.0, 5)
+    base, dP = s_alpha_base(0.8, 0.8, theta)
+    R = shc.host_scan_solve(lib, base[None], np.array([dP]), th0[None], theta[1] - theta[0])
+    assert np.all((R["info"] >> 16) == 0)
+    for t, t0 in enumerate(th0):
+        gam, X, dX, *_ = bo.gamma_ball_full(dP, theta, base[0], base[1], base[2] + t0 * base[3],
+                                            base[4] + 2 * t0 * base[5] + t0 ** 2 * base[6], method="lambda_max")
+        X = X * np.sign(X[np.argmax(np.abs(X))])
+        assert abs(R["lam"][0, t] - gam) <= LAM_RTOL * abs(gam)
+        np.testing.assert_allclose(R["X"][t], X, rtol=0, atol=X_ATOL)

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import LAM_RTOL, X_ATOL, fixture_base, sign_normalise
+from helpers import LAM_RTOL, X_ATOL, fixture_base, s_alpha_base, sign_normalise
 
 pytestmark = pytest.mark.gpu
 
@@ -109,3 +109,49 @@ def test_scan_kernel_outputs_optional_and_bad_input(cuda_lib, golden):
     fl = full.flags.cpu().numpy()
     assert np.all(fl[:9] == 0) and np.all(fl[9:] == 2)
     assert torch.isnan(full.lam[9:]).all() and torch.all(full.X[9:] == 0)
+
+
+def test_scan_kernel_moves_matching_row(cuda_lib):
+    """s-alpha lines with theta0 spread over [0, 20]: the 32 lanes of a warp have their eigenfunction peaks up to 600 rows
+    apart, so no single matching row suits all of them -- the low-quality fallback (matching row moved, open solves
+    re-converged) has to deliver every solve to full accuracy."""
+    import torch
+    from ideal_ballooning_solver_b200 import engine
+    from oracle import ballooning_oracle as bo
+    theta = np.linspace(-10 * np.pi, 10 * np.pi, 2049)
+    h = engine.grid_spacing(theta)
+    cases = [(0.8, 0.8), (1.2, 0.4), (0.4, 0.6)]
+    t0 = np.linspace(0.0, 20.0, 40)
+    bases, dPs = zip(*[s_alpha_base(s, a, theta) for s, a in cases])
+    base = torch.from_numpy(np.array(bases)).cuda()
+    dP = torch.from_numpy(np.array(dPs)).cuda()
+    th0 = torch.from_numpy(np.tile(t0, len(cases))).cuda()
+    new = _solve(base, dP, th0, h, len(t0), True)
+    old = _solve(base, dP, th0, h, len(t0), False)
+    assert np.all(new.flags.cpu().numpy() == 0) and np.all(old.flags.cpu().numpy() == 0)
+    np.testing.assert_allclose(new.lam.cpu().numpy(), old.lam.cpu().numpy(), rtol=LAM_RTOL, atol=0)
+    np.testing.assert_allclose(new.X.cpu().numpy(), old.X.cpu().numpy(), rtol=0, atol=X_ATOL)
+    assert np.ptp(np.argmax(new.X.cpu().numpy(), axis=1)) > 400          # the peaks really are far apart
+    lam = new.lam.cpu().numpy()
+    for s in (0, 17, 39, 40 + 25, 80 + 39):
+        i, t = divmod(s, len(t0))
+        b = bases[i]
+        gam, X, *_ = bo.gamma_ball_full(dPs[i], theta, b[0], b[1], b[2] + t0[t] * b[3], b[4] + 2 * t0[t] * b[5] + t0[t] ** 2 * b[6],
+                                        method="lambda_max")
+        assert abs(lam[s] - gam) <= LAM_RTOL * abs(gam)
+        np.testing.assert_allclose(new.X[s].cpu().numpy(), sign_normalise(X), rtol=0, atol=X_ATOL)
+
+
+def test_scan_kernel_ineligible_batches_use_team_kernel(cuda_lib, golden):
+    """Even N, fewer than four theta0, caller warm starts: not handled by the lane kernel -- the dispatch must fall back
+    to the team kernel (same results either way)."""
+    import torch
+    from ideal_ballooning_solver_b200 import engine
+    D = golden("synthetic_d3d")
+    theta = D["theta"][:-1]                                   # 1024 points: even
+    h = engine.grid_spacing(theta)
+    fb = fixture_base(D).reshape(-1, 8, len(D["theta"]))[:, :, :-1].copy()
+    th0 = torch.from_numpy(np.tile(np.linspace(0, 1, 6), fb.shape[0])).cuda()
+    a = _solve(torch.from_numpy(fb).cuda(), torch.from_numpy(D["dPdrho"].reshape(-1)).cuda(), th0, h, 6, True)
+    b = _solve(torch.from_numpy(fb).cuda(), torch.from_numpy(D["dPdrho"].reshape(-1)).cuda(), th0, h, 6, False)
+    assert torch.equal(a.lam, b.lam) and torch.equal(a.X, b.X)
