@@ -88,6 +88,8 @@ class ClockSampler:
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        if os.environ.get("IBS_BENCH_NO_SAMPLER"):       # diagnostic: is a slow step caused by the nvidia-smi queries?
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
@@ -208,11 +210,13 @@ def describe(workload, equilibria):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="d3d", choices=sorted(WORKLOADS))
-    ap.add_argument("--equilibria", type=int, default=16, help="independent equilibria batched per step per GPU")
+    ap.add_argument("--equilibria", type=int, default=37,
+                    help="independent equilibria batched per step per GPU (37 x 128 lines x 2 theta0 groups = 9472 items = 8 full rounds "
+                         "of the 148 x 8 resident warps of the solver kernel; 16 leaves the last of 3.5 rounds half empty: -12%%)")
     ap.add_argument("--chain", type=int, default=-1, help="warm-start run length over theta0 (-1 = scan default, 1 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -345,7 +349,8 @@ def main():
     rf = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.isfile(rf):
         try:
-            traffic = json.load(open(rf)).get(args.workload, {}).get("dram_bytes_per_launch")
+            per_solve = json.load(open(rf)).get(args.workload, {}).get("dram_bytes_per_solve")
+            traffic = None if per_solve is None else float(per_solve) * nsolve
         except Exception:
             traffic = None
     line = {

@@ -871,8 +871,13 @@ template <int SPL> struct ColdStride { static constexpr int value = (int)((sizeo
 //          then X (stored raw by O1) is normalised and dX formed by the context's fix-up (coalesced over the rows)
 //   SIGMA  one count at 2 sigma - lambda (utils.py:1597 returns the eigenvalue nearest sigma; the engine lambda_max)
 enum { PH_ITER = 0, PH_PEAK = 1, PH_O1 = 2, PH_O2 = 3, PH_SIGMA = 4 };
+// MODE_FULL: everything.  The two-kernel form splits it where the register needs differ (the iteration needs about half
+// of what the output passes need): MODE_ITER = the level iterations only (matching row = middle row; res[].rho / .info
+// carry the converged shift and the counters out), MODE_OUT = output passes, fallback and sigma check, started from the
+// res[].rho / .info of a MODE_ITER run.
+enum { MODE_FULL = 0, MODE_ITER = 1, MODE_OUT = 2 };
 
-template <int SPL, class Ctx>
+template <int SPL, int MODE, class Ctx>
 IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL], const bool (&act)[SPL], const double (&sigma)[SPL],
                        const bool has_sigma, double* const (&Xrow)[SPL], double* const (&dXrow)[SPL], ItemResult (&res)[SPL],
                        ColdState<SPL>& cs) {
@@ -898,11 +903,16 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
     for (int q = 0; q < SPL; ++q) {
         Xraw[q] = nullptr;
         rho1[q] = qnan; rho2[q] = qnan; nev[q] = 0; flags[q] = 0; fin[q] = false; wr[q] = false; need[q] = false; o1at[q] = false; rbest[q] = qnan; Kest[q] = 1e300;
-        res[q].gam = qnan; res[q].rho = qnan;
         iter_init(it[q], qnan, P.Lb, P.U, false);
         sh[q] = it[q].lam;
+        if (MODE == MODE_OUT) {          // continue a MODE_ITER run
+            sh[q] = res[q].rho; rbest[q] = res[q].rho;
+            flags[q] = res[q].info >> 16; nev[q] = (res[q].info & 0xffff) << MAXLEV;
+        }
+        res[q].gam = qnan; res[q].rho = qnan;
     }
-    int lev = P.nlev, Nl = level_n(N, lev), k = clamp_k((Nl - 1) / 2, Nl), round = 0, phase = PH_ITER;
+    int lev = (MODE == MODE_OUT) ? 0 : P.nlev, Nl = level_n(N, lev), k = clamp_k((Nl - 1) / 2, Nl), round = 0;
+    int phase = (MODE == MODE_OUT) ? PH_O1 : PH_ITER;
     bool lowq_any = false;
     int jsel = -1;
     bool fix_any = false;
@@ -921,7 +931,7 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
         }
         const int kind = (phase == PH_ITER) ? (o1it ? 2 : 1) : (phase == PH_SIGMA) ? 1 : (phase == PH_PEAK) ? 2 :
                          (phase == PH_O1) ? (skip_o1 ? 0 : 2) : 3;
-        if (kind == 1) eval_pass<SPL>(ctx, lev, Nl, k, th0, sh, r, S, nodes);
+        if (kind == 1 || MODE == MODE_ITER) eval_pass<SPL>(ctx, lev, Nl, k, th0, sh, r, S, nodes);
         else if (kind == 2) out_pass<SPL, false>(ctx, lev, Nl, k, th0, sh, out, Xraw);
         else if (kind == 3) out_pass<SPL, true>(ctx, lev, Nl, k, th0, sh, out, Xraw);
         // ---- what the phase does with it
@@ -956,7 +966,7 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
                     // quadratic convergence e_{n+1} = K e_n^2: K from the last two corrections of this level (if it has two)
                     Kest[q] = (it[q].dprev2 < 1e299 && it[q].dprev2 > 0.0 && it[q].dprev > tol) ? it[q].dprev / (it[q].dprev2 * it[q].dprev2) : 1e300;
                 }
-                if (lev == P.nlev) {
+                if (MODE != MODE_ITER && lev == P.nlev) {
 #pragma unroll
                     for (int q = 0; q < SPL; ++q) sh[q] = (rho1[q] == rho1[q]) ? rho1[q] : it[q].lam;
                     phase = PH_PEAK;
@@ -977,6 +987,11 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
                         keep = keep && ok1;
                         if (!it[q].conv) flags[q] |= FLAG_NOT_CONVERGED;
                     }
+                if (MODE == MODE_ITER) {
+#pragma unroll
+                    for (int q = 0; q < SPL; ++q) res[q].rho = rbest[q];
+                    break;
+                }
                 skip_o1 = ctx.all(keep);
                 phase = PH_O1;
                 continue;

@@ -39,6 +39,7 @@ struct ScanParams {
     double h;
     double* lam_out; double* lam_matrix_out; double* X_out; double* dX_out; int* info_out;
     double* X_rows;           // where the eigenfunctions go: X_out, or scratch when only dX is wanted (null: no eigenfunction output)
+    double* shift_ws; int* info_ws;      // two-kernel form: converged shift and counters handed from the iteration kernel to the output kernel
     unsigned* counter;
 };
 
@@ -127,8 +128,11 @@ struct DevCtx {
     }
 };
 
-template <int SPL>
-__global__ void __launch_bounds__(SC_WARPS * 32, (SPL == 1) ? IBS_SCAN_CTAS1 : 2)
+#ifndef IBS_SCAN_CTAS_ITER
+#define IBS_SCAN_CTAS_ITER 3     // CTAs per SM the iteration-only kernel (two-kernel form) is compiled for
+#endif
+template <int SPL, int MODE>
+__global__ void __launch_bounds__(SC_WARPS * 32, (MODE == MODE_ITER) ? IBS_SCAN_CTAS_ITER : ((SPL == 1) ? IBS_SCAN_CTAS1 : 2))
 scan_solve_kernel(const ScanParams p) {
     extern __shared__ __align__(128) double sc_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -170,13 +174,22 @@ scan_solve_kernel(const ScanParams p) {
         P.want_X = p.X_rows != nullptr; P.want_dX = p.dX_out != nullptr;
         ctx.line_base = p.poly + (size_t)line * p.rows_total * REC;
         ItemResult res[SPL];
-        solve_item<SPL>(ctx, P, th0, act, sg, p.sigma != nullptr, Xrow, dXrow, res, cold);
+        if (MODE == MODE_OUT) {
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) { res[q].rho = p.shift_ws[sidx[q]]; res[q].info = p.info_ws[sidx[q]]; res[q].gam = 0.0; }
+        }
+        solve_item<SPL, MODE>(ctx, P, th0, act, sg, p.sigma != nullptr, Xrow, dXrow, res, cold);
 #pragma unroll
         for (int q = 0; q < SPL; ++q)
             if (act[q]) {
-                p.lam_out[sidx[q]] = res[q].gam;
-                if (p.lam_matrix_out) p.lam_matrix_out[sidx[q]] = res[q].rho;
-                if (p.info_out) p.info_out[sidx[q]] = res[q].info;
+                if (MODE == MODE_ITER) {           // hand over to the output kernel
+                    p.shift_ws[sidx[q]] = res[q].rho;
+                    p.info_ws[sidx[q]] = res[q].info;
+                } else {
+                    p.lam_out[sidx[q]] = res[q].gam;
+                    if (p.lam_matrix_out) p.lam_matrix_out[sidx[q]] = res[q].rho;
+                    if (p.info_out) p.info_out[sidx[q]] = res[q].info;
+                }
             }
     }
 }
@@ -269,9 +282,9 @@ bool scan_solver_eligible(const SolveParams& p) {
     return true;
 }
 
-template <int SPL>
+template <int SPL, int MODE>
 static int scan_launch(const ScanParams& sp, cudaStream_t stream) {
-    auto kern = scan_solve_kernel<SPL>;
+    auto kern = scan_solve_kernel<SPL, MODE>;
     const size_t smem = (size_t)SC_WARPS * SC_RING * sizeof(double) + (size_t)SC_WARPS * SC_NSTAGE * sizeof(uint64_t) +
                         (size_t)SC_WARPS * 32 * ColdStride<SPL>::value * sizeof(double);
     static bool configured = false;
@@ -303,7 +316,12 @@ int scan_solve_dispatch(const SolveParams& p, cudaStream_t stream) {
     const size_t poly_bytes = (size_t)nline * rows_total * REC * sizeof(double);
     const size_t bounds_off = (poly_bytes + 255) & ~(size_t)255;
     const size_t counter_off = bounds_off + (((size_t)nline * 2 * sizeof(double) + 255) & ~(size_t)255);
-    const size_t xs_off = counter_off + 256;
+    // two-kernel form (IBS_SCAN_TWO=1): iteration kernel (fewer registers, more resident warps) + output kernel
+    bool two = false;
+    if (const char* e = std::getenv("IBS_SCAN_TWO")) two = std::atoi(e) != 0;
+    const size_t hand_off = counter_off + 256;
+    const size_t hand_bytes = two ? ((((size_t)p.nsolve * (sizeof(double) + sizeof(int))) + 255) & ~(size_t)255) : 0;
+    const size_t xs_off = hand_off + hand_bytes;
     const size_t xs_bytes = (p.dX_out && !p.X_out) ? (size_t)p.nsolve * N * sizeof(double) : 0;      // X is the scratch dX is formed from
     char* ws = nullptr;
     IBS_CUDA_CHECK(cudaMallocAsync((void**)&ws, xs_off + xs_bytes + 256, stream));
@@ -317,13 +335,22 @@ int scan_solve_dispatch(const SolveParams& p, cudaStream_t stream) {
     sp.h = p.h;
     sp.lam_out = p.lam_out; sp.lam_matrix_out = p.lam_matrix_out; sp.X_out = p.X_out; sp.dX_out = p.dX_out; sp.info_out = p.info_out;
     sp.X_rows = p.X_out ? p.X_out : (xs_bytes ? (double*)(ws + xs_off) : nullptr);
-    if (cudaMemsetAsync(sp.counter, 0, sizeof(unsigned), stream) != cudaSuccess) rc = IBS_ERR_CUDA;
+    sp.shift_ws = two ? (double*)(ws + hand_off) : nullptr;
+    sp.info_ws = two ? (int*)(ws + hand_off + (size_t)p.nsolve * sizeof(double)) : nullptr;
+    if (cudaMemsetAsync(sp.counter, 0, 2 * sizeof(unsigned), stream) != cudaSuccess) rc = IBS_ERR_CUDA;
     if (rc == IBS_OK) {
         scan_prep_kernel<<<nline, PREP_T, 0, stream>>>(p.base, p.dPdrho, p.theta0, p.nth0, N, p.h * p.h, nlev, rows_total,
                                                        (double*)ws, (double*)(ws + bounds_off));
         if (cudaGetLastError() != cudaSuccess) { set_error("scan_prep_kernel launch failed"); rc = IBS_ERR_CUDA; }
     }
-    if (rc == IBS_OK) rc = (spl == 2) ? scan_launch<2>(sp, stream) : scan_launch<1>(sp, stream);
+    if (rc == IBS_OK) {
+        if (two && spl == 1) {
+            rc = scan_launch<1, MODE_ITER>(sp, stream);
+            if (rc == IBS_OK) { ScanParams sp2 = sp; sp2.counter = sp.counter + 1; rc = scan_launch<1, MODE_OUT>(sp2, stream); }
+        } else {
+            rc = (spl == 2) ? scan_launch<2, MODE_FULL>(sp, stream) : scan_launch<1, MODE_FULL>(sp, stream);
+        }
+    }
     cudaFreeAsync(ws, stream);
     return rc;
 }

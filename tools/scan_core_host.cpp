@@ -11,6 +11,8 @@
 
 using namespace ibs::scan;
 static double g_cost = 0.0;
+static bool two_kernel = false;
+extern "C" void scan_host_set_two_kernel(int v) { two_kernel = v != 0; }
 
 namespace {
 struct HostCtx {
@@ -110,7 +112,12 @@ extern "C" long scan_host_solve(const double* poly, const double* bounds, const 
             double* const dXrow[1] = {dX_out ? dX_out + s * N : nullptr};
             ItemResult res[1];
             ColdState<1> cold;
-            solve_item<1>(ctx, P, th0, act, sg, sigma != nullptr, Xrow, dXrow, res, cold);
+            if (two_kernel) {       // the two-kernel form: iterate, then the output passes from the handed-over shift
+                solve_item<1, MODE_ITER>(ctx, P, th0, act, sg, false, Xrow, dXrow, res, cold);
+                solve_item<1, MODE_OUT>(ctx, P, th0, act, sg, sigma != nullptr, Xrow, dXrow, res, cold);
+            } else {
+                solve_item<1, MODE_FULL>(ctx, P, th0, act, sg, sigma != nullptr, Xrow, dXrow, res, cold);
+            }
             lam_out[s] = res[0].gam;
             if (lam_matrix_out) lam_matrix_out[s] = res[0].rho;
             if (info_out) info_out[s] = res[0].info;

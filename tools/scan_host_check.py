@@ -33,6 +33,8 @@ def build(outdir="/tmp/sch"):
     lib.scan_host_solve.restype = ctypes.c_long
     lib.scan_host_last_cost.restype = ctypes.c_double
     lib.scan_host_solve.argtypes = [dp, dp, dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, dp, dp, dp, ip]
+    if os.environ.get("IBS_SCAN_TWO"):
+        lib.scan_host_set_two_kernel(int(os.environ["IBS_SCAN_TWO"]))
     return lib
 
 
