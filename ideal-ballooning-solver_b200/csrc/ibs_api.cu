@@ -1,4 +1,5 @@
 // C ABI of the library (see include/ibs_b200.h).  Thin argument checking + dispatch; no torch types.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -64,6 +65,19 @@ void keep_pool_cached() {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     done[dev] = true;
+}
+
+// theta0 of every solve of a scan (theta0 fastest): t0[i] = theta0[i % nth0]
+__global__ void replicate_theta0_kernel(const double* __restrict__ theta0, int nth0, long long n, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = theta0[i % nth0];
+}
+// number of solves flagged not-converged / bad-input
+__global__ void count_bad_kernel(const int* __restrict__ info, long long n, int* __restrict__ count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = i < n && ((info[i] >> 16) & (IBS_FLAG_NOT_CONVERGED | IBS_FLAG_BAD_INPUT));
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
 }
 
 static SolveParams blank_params() { SolveParams p; std::memset(&p, 0, sizeof(p)); return p; }
@@ -207,75 +221,125 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
     IBS_REQUIRE(tab_mn && tab_nyq && scal && alpha && theta0 && theta && gamma_out, "null pointer");
     IBS_REQUIRE(ns >= 1 && nalpha >= 1 && nth0 >= 1 && nl >= 3, "bad sizes");
     keep_pool_cached();
-    cudaStream_t st = nullptr;
+    // Three streams: uploads, compute, downloads.  The surfaces are processed in chunks (every chunk: tables up ->
+    // K1 -> K2+K3 -> arg-max -> eigenfunction of each surface's maximum -> results down), so that the copies of one chunk
+    // overlap the kernels of its neighbours; a chunk keeps >= 4 rounds of the solver's resident warps busy (measured on
+    // the D3D config x 37 equilibria: 1 / 2 / 4 chunks = 3.37e7 / 3.55e7 / 3.22e7 solves/s; IBS_HOST_CHUNKS overrides).
+    cudaStream_t st_h = nullptr, st = nullptr, st_d = nullptr;
+    IBS_CUDA_CHECK(cudaStreamCreateWithFlags(&st_h, cudaStreamNonBlocking));
     IBS_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    IBS_CUDA_CHECK(cudaStreamCreateWithFlags(&st_d, cudaStreamNonBlocking));
     const size_t nlines = (size_t)ns * nalpha, nsolve = nlines * nth0;
-    const size_t b_tab_mn = (size_t)ns * 6 * mnmax * 8, b_tab_nyq = (size_t)ns * 7 * mnmax_nyq * 8, b_scal = (size_t)ns * IBS_NSCAL * 8;
-    // one device arena: inputs | base | dPdrho | theta0 per solve | gamma | val | sigma0 | idx | info
+    const int ngrid = nalpha * nth0;
+    int nchunk = 1;
+    {
+        const long long items = (long long)nlines * ((nth0 + 31) / 32), per_round = 8LL * num_sms();
+        nchunk = (int)(items / (4 * per_round));
+        if (const char* e = std::getenv("IBS_HOST_CHUNKS")) nchunk = std::atoi(e);
+        if (nchunk > 8) nchunk = 8;
+        if (nchunk > ns) nchunk = ns;
+        if (nchunk < 1) nchunk = 1;
+    }
+    const size_t r_mn = (size_t)6 * mnmax * 8, r_nyq = (size_t)7 * mnmax_nyq * 8, r_sc = (size_t)IBS_NSCAL * 8;      // bytes per surface
+    // one device arena: inputs | base | dPdrho | theta0 per solve | gamma | val | sigma0 | idx | info | best-solve scratch
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_tmn = take(b_tab_mn), o_tnq = take(b_tab_nyq), o_sc = take(b_scal), o_al = take((size_t)nalpha * 8),
+    const size_t o_tmn = take(ns * r_mn), o_tnq = take(ns * r_nyq), o_sc = take(ns * r_sc), o_al = take((size_t)nalpha * 8),
                  o_th = take((size_t)nl * 8), o_t0 = take(nsolve * 8), o_base = take(nlines * IBS_NBASE * nl * 8),
                  o_dp = take(nlines * 8), o_gam = take(nsolve * 8), o_val = take((size_t)ns * 8), o_sig = take((size_t)ns * 8),
                  o_idx = take((size_t)ns * 4), o_info = take(nsolve * 4),
                  o_xb = take(xbest_out ? (size_t)ns * nl * 8 : 0), o_bl = take((size_t)ns * 4), o_bt = take((size_t)ns * 8),
-                 o_bg = take((size_t)ns * 8);
+                 o_bg = take((size_t)ns * 8), o_t0h = take((size_t)nth0 * 8), o_nb = take(4);
     char* d = nullptr;
     int rc = IBS_OK;
-    std::vector<double> t0_rep(nsolve);
-    for (size_t i = 0; i < nsolve; ++i) t0_rep[i] = theta0[i % nth0];
-    std::vector<int> info(nsolve);
+    int nbad_host = 0;
+    std::vector<cudaEvent_t> ev_h(nchunk, nullptr), ev_c(nchunk, nullptr);
+    cudaEvent_t ev_alloc = nullptr, ev_done = nullptr;
 #define IBS_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { rc = cuda_fail(_e, #expr); goto done; } } while (0)
+    for (int c = 0; c < nchunk; ++c) {
+        IBS_TRY(cudaEventCreateWithFlags(&ev_h[c], cudaEventDisableTiming));
+        IBS_TRY(cudaEventCreateWithFlags(&ev_c[c], cudaEventDisableTiming));
+    }
+    IBS_TRY(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+    IBS_TRY(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
     IBS_TRY(cudaMallocAsync((void**)&d, off, st));
-    IBS_TRY(cudaMemcpyAsync(d + o_tmn, tab_mn, b_tab_mn, cudaMemcpyHostToDevice, st));
-    IBS_TRY(cudaMemcpyAsync(d + o_tnq, tab_nyq, b_tab_nyq, cudaMemcpyHostToDevice, st));
-    IBS_TRY(cudaMemcpyAsync(d + o_sc, scal, b_scal, cudaMemcpyHostToDevice, st));
-    IBS_TRY(cudaMemcpyAsync(d + o_al, alpha, (size_t)nalpha * 8, cudaMemcpyHostToDevice, st));
-    IBS_TRY(cudaMemcpyAsync(d + o_th, theta, (size_t)nl * 8, cudaMemcpyHostToDevice, st));
-    IBS_TRY(cudaMemcpyAsync(d + o_t0, t0_rep.data(), nsolve * 8, cudaMemcpyHostToDevice, st));
-    rc = geometry_dispatch((double*)(d + o_tmn), (double*)(d + o_tnq), (double*)(d + o_sc), xm, xn, xm_nyq, xn_nyq, ns, mnmax,
-                           mnmax_nyq, phiedge, aminor_p, (double*)(d + o_al), nalpha, 0, (double*)(d + o_th), nl, 0.0,
-                           (double*)(d + o_base), (double*)(d + o_dp), nullptr, nullptr, st);
-    if (rc != IBS_OK) goto done;
-    {
-        SolveParams p = blank_params();
-        p.base = (double*)(d + o_base); p.dPdrho = (double*)(d + o_dp); p.theta0 = (double*)(d + o_t0); p.nth0 = nth0;
-        p.nsolve = (int)nsolve; p.N = nl; p.h = h; p.lam_out = (double*)(d + o_gam); p.info_out = (int*)(d + o_info);
-        p.chain_len = scan_chain_len(nth0);
-        rc = solve_dispatch(p, true, false, st);
-        if (rc != IBS_OK) goto done;
+    IBS_TRY(cudaEventRecord(ev_alloc, st));
+    IBS_TRY(cudaStreamWaitEvent(st_h, ev_alloc, 0));
+    IBS_TRY(cudaStreamWaitEvent(st_d, ev_alloc, 0));
+    // ---- uploads: the small arrays first, then the tables chunk by chunk
+    IBS_TRY(cudaMemcpyAsync(d + o_al, alpha, (size_t)nalpha * 8, cudaMemcpyHostToDevice, st_h));
+    IBS_TRY(cudaMemcpyAsync(d + o_th, theta, (size_t)nl * 8, cudaMemcpyHostToDevice, st_h));
+    IBS_TRY(cudaMemcpyAsync(d + o_t0h, theta0, (size_t)nth0 * 8, cudaMemcpyHostToDevice, st_h));
+    replicate_theta0_kernel<<<(unsigned)((nsolve + 255) / 256), 256, 0, st_h>>>((double*)(d + o_t0h), nth0, (long long)nsolve, (double*)(d + o_t0));
+    IBS_TRY(cudaGetLastError());
+    IBS_TRY(cudaMemsetAsync(d + o_nb, 0, 4, st_h));
+    for (int c = 0; c < nchunk; ++c) {
+        const size_t s0 = (size_t)ns * c / nchunk, nsc = (size_t)ns * (c + 1) / nchunk - s0;
+        IBS_TRY(cudaMemcpyAsync(d + o_tmn + s0 * r_mn, (const char*)tab_mn + s0 * r_mn, nsc * r_mn, cudaMemcpyHostToDevice, st_h));
+        IBS_TRY(cudaMemcpyAsync(d + o_tnq + s0 * r_nyq, (const char*)tab_nyq + s0 * r_nyq, nsc * r_nyq, cudaMemcpyHostToDevice, st_h));
+        IBS_TRY(cudaMemcpyAsync(d + o_sc + s0 * r_sc, (const char*)scal + s0 * r_sc, nsc * r_sc, cudaMemcpyHostToDevice, st_h));
+        IBS_TRY(cudaEventRecord(ev_h[c], st_h));
     }
-    rc = launch_argmax((double*)(d + o_gam), ns, nalpha * nth0, (double*)(d + o_val), (int*)(d + o_idx), (double*)(d + o_sig), st);
-    if (rc != IBS_OK) goto done;
-    if (xbest_out) {
-        // eigenfunction of each surface's arg-max only: re-solve those ns problems with the eigenvector written out
-        // (instead of writing nsolve eigenvectors and gathering ns of them)
-        rc = launch_best_setup((int*)(d + o_idx), (double*)(d + o_t0), ns, nalpha * nth0, nth0, (int*)(d + o_bl), (double*)(d + o_bt), st);
+    // ---- compute + downloads, chunk by chunk
+    for (int c = 0; c < nchunk; ++c) {
+        const size_t s0 = (size_t)ns * c / nchunk, nsc = (size_t)ns * (c + 1) / nchunk - s0;
+        const size_t l0 = s0 * nalpha, nlc = nsc * nalpha, v0 = l0 * nth0, nvc = nlc * nth0;
+        double* base_c = (double*)(d + o_base) + l0 * IBS_NBASE * nl;
+        double* dp_c = (double*)(d + o_dp) + l0;
+        IBS_TRY(cudaStreamWaitEvent(st, ev_h[c], 0));
+        rc = geometry_dispatch((double*)(d + o_tmn + s0 * r_mn), (double*)(d + o_tnq + s0 * r_nyq), (double*)(d + o_sc + s0 * r_sc), xm, xn,
+                               xm_nyq, xn_nyq, (int)nsc, mnmax, mnmax_nyq, phiedge, aminor_p, (double*)(d + o_al), nalpha, 0,
+                               (double*)(d + o_th), nl, 0.0, base_c, dp_c, nullptr, nullptr, st);
         if (rc != IBS_OK) goto done;
-        SolveParams pb = blank_params();
-        pb.base = (double*)(d + o_base); pb.dPdrho = (double*)(d + o_dp); pb.theta0 = (double*)(d + o_bt);
-        pb.line_of_solve = (int*)(d + o_bl); pb.nth0 = 1; pb.nsolve = ns; pb.N = nl; pb.h = h;
-        pb.lam_out = (double*)(d + o_bg); pb.X_out = (double*)(d + o_xb);
-        rc = solve_dispatch(pb, true, false, st);
+        {
+            SolveParams p = blank_params();
+            p.base = base_c; p.dPdrho = dp_c; p.theta0 = (double*)(d + o_t0) + v0; p.nth0 = nth0;
+            p.nsolve = (int)nvc; p.N = nl; p.h = h; p.lam_out = (double*)(d + o_gam) + v0; p.info_out = (int*)(d + o_info) + v0;
+            p.chain_len = scan_chain_len(nth0);
+            rc = solve_dispatch(p, true, false, st);
+            if (rc != IBS_OK) goto done;
+        }
+        rc = launch_argmax((double*)(d + o_gam) + v0, (int)nsc, ngrid, (double*)(d + o_val) + s0, (int*)(d + o_idx) + s0,
+                           (double*)(d + o_sig) + s0, st);
         if (rc != IBS_OK) goto done;
-        IBS_TRY(cudaMemcpyAsync(xbest_out, d + o_xb, (size_t)ns * nl * 8, cudaMemcpyDeviceToHost, st));
+        if (xbest_out) {
+            // eigenfunction of each surface's arg-max only: re-solve those problems with the eigenvector written out
+            // (instead of writing nsolve eigenvectors and gathering ns of them); line indices are chunk-local
+            rc = launch_best_setup((int*)(d + o_idx) + s0, (double*)(d + o_t0) + v0, (int)nsc, ngrid, nth0, (int*)(d + o_bl) + s0,
+                                   (double*)(d + o_bt) + s0, st);
+            if (rc != IBS_OK) goto done;
+            SolveParams pb = blank_params();
+            pb.base = base_c; pb.dPdrho = dp_c; pb.theta0 = (double*)(d + o_bt) + s0;
+            pb.line_of_solve = (int*)(d + o_bl) + s0; pb.nth0 = 1; pb.nsolve = (int)nsc; pb.N = nl; pb.h = h;
+            pb.lam_out = (double*)(d + o_bg) + s0; pb.X_out = (double*)(d + o_xb) + s0 * nl;
+            rc = solve_dispatch(pb, true, false, st);
+            if (rc != IBS_OK) goto done;
+        }
+        count_bad_kernel<<<(unsigned)((nvc + 255) / 256), 256, 0, st>>>((int*)(d + o_info) + v0, (long long)nvc, (int*)(d + o_nb));
+        IBS_TRY(cudaGetLastError());
+        IBS_TRY(cudaEventRecord(ev_c[c], st));
+        IBS_TRY(cudaStreamWaitEvent(st_d, ev_c[c], 0));
+        IBS_TRY(cudaMemcpyAsync(gamma_out + v0, d + o_gam + v0 * 8, nvc * 8, cudaMemcpyDeviceToHost, st_d));
+        if (val_out) IBS_TRY(cudaMemcpyAsync(val_out + s0, d + o_val + s0 * 8, nsc * 8, cudaMemcpyDeviceToHost, st_d));
+        if (idx_out) IBS_TRY(cudaMemcpyAsync(idx_out + s0, d + o_idx + s0 * 4, nsc * 4, cudaMemcpyDeviceToHost, st_d));
+        if (sigma0_out) IBS_TRY(cudaMemcpyAsync(sigma0_out + s0, d + o_sig + s0 * 8, nsc * 8, cudaMemcpyDeviceToHost, st_d));
+        if (xbest_out) IBS_TRY(cudaMemcpyAsync(xbest_out + s0 * nl, d + o_xb + s0 * nl * 8, nsc * nl * 8, cudaMemcpyDeviceToHost, st_d));
     }
-    IBS_TRY(cudaMemcpyAsync(gamma_out, d + o_gam, nsolve * 8, cudaMemcpyDeviceToHost, st));
-    if (val_out) IBS_TRY(cudaMemcpyAsync(val_out, d + o_val, (size_t)ns * 8, cudaMemcpyDeviceToHost, st));
-    if (idx_out) IBS_TRY(cudaMemcpyAsync(idx_out, d + o_idx, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
-    if (sigma0_out) IBS_TRY(cudaMemcpyAsync(sigma0_out, d + o_sig, (size_t)ns * 8, cudaMemcpyDeviceToHost, st));
-    IBS_TRY(cudaMemcpyAsync(info.data(), d + o_info, nsolve * 4, cudaMemcpyDeviceToHost, st));
-    IBS_TRY(cudaStreamSynchronize(st));
-    if (nbad_out) {
-        int nb = 0;
-        for (size_t i = 0; i < nsolve; ++i) nb += ((info[i] >> 16) & (IBS_FLAG_NOT_CONVERGED | IBS_FLAG_BAD_INPUT)) ? 1 : 0;
-        *nbad_out = nb;
-    }
+    IBS_TRY(cudaMemcpyAsync(&nbad_host, d + o_nb, 4, cudaMemcpyDeviceToHost, st_d));
+    IBS_TRY(cudaEventRecord(ev_done, st_d));
+    IBS_TRY(cudaStreamWaitEvent(st, ev_done, 0));          // the arena is freed (stream-ordered, on st) after the last download
+    IBS_TRY(cudaStreamSynchronize(st_d));
+    if (nbad_out) *nbad_out = nbad_host;
 done:
 #undef IBS_TRY
+    if (rc != IBS_OK) { cudaStreamSynchronize(st_h); cudaStreamSynchronize(st); cudaStreamSynchronize(st_d); }
     if (d) cudaFreeAsync(d, st);
     cudaStreamSynchronize(st);
-    cudaStreamDestroy(st);
+    for (auto e : ev_h) if (e) cudaEventDestroy(e);
+    for (auto e : ev_c) if (e) cudaEventDestroy(e);
+    if (ev_alloc) cudaEventDestroy(ev_alloc);
+    if (ev_done) cudaEventDestroy(ev_done);
+    cudaStreamDestroy(st_h); cudaStreamDestroy(st); cudaStreamDestroy(st_d);
     return rc;
 }
 
