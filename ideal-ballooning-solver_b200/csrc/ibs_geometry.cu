@@ -175,24 +175,47 @@ geometry_kernel(const GeoParams p) {
             }
             double th = theta_p;
             int nit = 0; bool ok = false;
+            double dprev = 1e300;
             for (nit = 1; nit <= 25; ++nit) {
                 double s1, c1;
                 sincos(th, &s1, &c1);
                 double cm = 1.0, sm = 0.0, fsum = 0.0, dsum = 0.0;
-                for (int m = 0; m < p.M1; ++m) {
-                    const double a = (NT1 > 0) ? Am[m] : s_mn[(size_t)m * ROW_MN + 6];
-                    const double b = (NT1 > 0) ? Bm[m] : 0.0;
-                    fsum = fma(sm, a, fsum); fsum = fma(-cm, b, fsum);
-                    const double dm = (double)m;
-                    dsum = fma(dm * cm, a, dsum); dsum = fma(dm * sm, b, dsum);
-                    const double cnx = fma(cm, c1, -(sm * s1));
-                    sm = fma(sm, c1, cm * s1);
-                    cm = cnx;
+                if constexpr (NT1 == 0) {
+                    // axisymmetric tables (n = 0 only): B_m = 0, no toroidal angle; 7 FP64 operations per mode
+                    double dm = 0.0;
+                    for (int m = 0; m < p.M1; ++m) {
+                        const double a = s_mn[(size_t)m * ROW_MN + 6];
+                        fsum = fma(sm, a, fsum);
+                        dsum = fma(dm * cm, a, dsum);
+                        const double cnx = fma(cm, c1, -(sm * s1));
+                        sm = fma(sm, c1, cm * s1);
+                        cm = cnx;
+                        dm += 1.0;
+                    }
+                } else {
+                    for (int m = 0; m < p.M1; ++m) {
+                        const double a = Am[m];
+                        const double b = Bm[m];
+                        fsum = fma(sm, a, fsum); fsum = fma(-cm, b, fsum);
+                        const double dm = (double)m;
+                        dsum = fma(dm * cm, a, dsum); dsum = fma(dm * sm, b, dsum);
+                        const double cnx = fma(cm, c1, -(sm * s1));
+                        sm = fma(sm, c1, cm * s1);
+                        cm = cnx;
+                    }
                 }
                 const double res = (th + fsum) - theta_p;
                 const double dth = res / (1.0 + dsum);
                 th -= dth;
-                if (fabs(dth) <= 4.5e-16 * fmax(1.0, fabs(th))) { ok = true; break; }
+                const double ad = fabs(dth), scale_th = fmax(1.0, fabs(th));
+                if (ad <= 4.5e-16 * scale_th) { ok = true; break; }
+                // quadratic convergence: the error left after this step is ~ ad^3 / dprev^2 -- no confirming iteration
+                // once that is below the rounding level
+                if (dprev < 1.0 && ad < 1e-3 * dprev) {           // (needs a previous correction, itself already small)
+                    const double q = ad / dprev;
+                    if (ad * q * q <= 2e-16 * scale_th) { ok = true; break; }
+                }
+                dprev = ad;
             }
             // ---- mode sums (utils.py:420-468)
             double s1, c1;
@@ -229,6 +252,30 @@ geometry_kernel(const GeoParams p) {
                     const double cnx = fma(cm, c1, -(sm * s1));
                     sm = fma(sm, c1, cm * s1);
                     cm = cnx;
+                }
+            } else if constexpr (NT1 == 0) {
+                // axisymmetric tables: one entry (n = 0) per m, the angle is m theta itself and the n-weighted sums
+                // (d/dphi) vanish: 10 FP64 operations per mode + the recurrence
+                double cm = 1.0, sm = 0.0, dm = 0.0;
+                for (int m = 0; m < p.M1; ++m) {
+                    const double* row = s_mn + (size_t)m * ROW_MN;
+                    const double2 v0 = *reinterpret_cast<const double2*>(row + 0);   // r, n r (= 0)
+                    const double2 v1 = *reinterpret_cast<const double2*>(row + 2);   // r_s, z
+                    const double2 v2 = *reinterpret_cast<const double2*>(row + 4);   // n z (= 0), z_s
+                    const double2 v3 = *reinterpret_cast<const double2*>(row + 6);   // l, n l (= 0)
+                    const double v4 = row[8];                                          // l_s
+                    const double msm = dm * sm, mcm = dm * cm;
+                    R = fma(v0.x, cm, R);
+                    R_t = fma(-v0.x, msm, R_t);
+                    R_s = fma(v1.x, cm, R_s);
+                    Z_t = fma(v1.y, mcm, Z_t);
+                    Z_s = fma(v2.y, sm, Z_s);
+                    L_t = fma(v3.x, mcm, L_t);
+                    L_s = fma(v4, sm, L_s);
+                    const double cnx = fma(cm, c1, -(sm * s1));
+                    sm = fma(sm, c1, cm * s1);
+                    cm = cnx;
+                    dm += 1.0;
                 }
             } else {
                 double cm = 1.0, sm = 0.0;
@@ -297,6 +344,27 @@ geometry_kernel(const GeoParams p) {
                     const double cnx = fma(cm, c1, -(sm * s1));
                     sm = fma(sm, c1, cm * s1);
                     cm = cnx;
+                }
+            } else if constexpr (NT2 == 0) {
+                double cm = 1.0, sm = 0.0, dm = 0.0;
+                for (int m = 0; m < p.M2; ++m) {
+                    const double* row = s_nyq + (size_t)m * ROW_NYQ;
+                    const double2 v0 = *reinterpret_cast<const double2*>(row + 0);  // g, b
+                    const double2 v1 = *reinterpret_cast<const double2*>(row + 2);  // n b (= 0), b_s
+                    const double2 v2 = *reinterpret_cast<const double2*>(row + 4);  // bsupv, bsubs
+                    const double2 v3 = *reinterpret_cast<const double2*>(row + 6);  // bsubu, bsubv
+                    sqrtg = fma(v0.x, cm, sqrtg);
+                    B = fma(v0.y, cm, B);
+                    B_t = fma(-v0.y, dm * sm, B_t);
+                    B_s = fma(v1.y, cm, B_s);
+                    Bsup_p = fma(v2.x, cm, Bsup_p);
+                    Bsub_s = fma(v2.y, sm, Bsub_s);
+                    Bsub_t = fma(v3.x, cm, Bsub_t);
+                    Bsub_p = fma(v3.y, cm, Bsub_p);
+                    const double cnx = fma(cm, c1, -(sm * s1));
+                    sm = fma(sm, c1, cm * s1);
+                    cm = cnx;
+                    dm += 1.0;
                 }
             } else {
                 double cm = 1.0, sm = 0.0;
