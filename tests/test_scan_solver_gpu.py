@@ -10,10 +10,11 @@ from helpers import LAM_RTOL, X_ATOL, fixture_base, s_alpha_base, sign_normalise
 pytestmark = pytest.mark.gpu
 
 
-def _solve(base, dP, th0, h, nth0, scan, spl=None, **kw):
+def _solve(base, dP, th0, h, nth0, scan, spl=None, two=False, **kw):
     from ideal_ballooning_solver_b200 import engine
-    old = {k: os.environ.get(k) for k in ("IBS_SCAN", "IBS_SCAN_SPL")}
+    old = {k: os.environ.get(k) for k in ("IBS_SCAN", "IBS_SCAN_SPL", "IBS_SCAN_TWO")}
     os.environ["IBS_SCAN"] = "1" if scan else "0"
+    os.environ["IBS_SCAN_TWO"] = "1" if two else "0"
     if spl:
         os.environ["IBS_SCAN_SPL"] = str(spl)
     try:
@@ -155,3 +156,24 @@ def test_scan_kernel_ineligible_batches_use_team_kernel(cuda_lib, golden):
     a = _solve(torch.from_numpy(fb).cuda(), torch.from_numpy(D["dPdrho"].reshape(-1)).cuda(), th0, h, 6, True)
     b = _solve(torch.from_numpy(fb).cuda(), torch.from_numpy(D["dPdrho"].reshape(-1)).cuda(), th0, h, 6, False)
     assert torch.equal(a.lam, b.lam) and torch.equal(a.X, b.X)
+
+
+@pytest.mark.parametrize("name", ["synthetic_d3d", "synthetic_ncsx"])
+def test_scan_kernel_two_kernel_form(cuda_lib, golden, name):
+    """IBS_SCAN_TWO=1: iteration kernel (fewer registers) + output kernel, the converged shift handed over in memory."""
+    import torch
+    from ideal_ballooning_solver_b200 import engine
+    D = golden(name)
+    theta = D["theta"]
+    h = engine.grid_spacing(theta)
+    fb = fixture_base(D)
+    ns, na = fb.shape[:2]
+    base, dP = torch.from_numpy(fb).cuda(), torch.from_numpy(D["dPdrho"]).cuda()
+    th0 = torch.from_numpy(np.tile(np.linspace(0.0, np.pi / 2, 37), ns * na)).cuda()
+    sigma = torch.full((th0.numel(),), 1.0, dtype=torch.float64)
+    one = _solve(base, dP, th0, h, 37, True, sigma=sigma)
+    two = _solve(base, dP, th0, h, 37, True, two=True, sigma=sigma)
+    assert np.all(two.flags.cpu().numpy() == one.flags.cpu().numpy())
+    np.testing.assert_allclose(two.lam.cpu().numpy(), one.lam.cpu().numpy(), rtol=LAM_RTOL, atol=0)
+    np.testing.assert_allclose(two.X.cpu().numpy(), one.X.cpu().numpy(), rtol=0, atol=X_ATOL)
+    np.testing.assert_allclose(two.dX.cpu().numpy(), one.dX.cpu().numpy(), rtol=0, atol=10 * X_ATOL * max(1.0, float(one.dX.abs().max())))
