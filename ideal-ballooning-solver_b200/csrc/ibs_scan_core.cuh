@@ -44,11 +44,10 @@ constexpr int MIN_COARSE_N = 65;  // a level is used only if it has at least thi
 constexpr int MAXIT_LEVEL = 64;   // evaluations per level before giving up
 constexpr int K_MARGIN = 8;       // matching row kept this far from both ends
 constexpr double LOWQ = 1.0e3;
-// Letting the output pass stand in for the last fine-level evaluation saves ~1 of ~6 fine-grid passes, but its vector is
-// then taken at a shift that is only ~1e-11 converged and the Simpson Rayleigh quotient (which weighs the far end of
-// the spectrum heavily) moves by up to 6e-11 relative: measured, no speed-up at warp level (the acceptance test has
-// to hold for all 32 lanes) -> off.
-constexpr bool OUT_PASS_AS_EVAL = false;
+// (Tried and removed: letting the output pass stand in for the last fine-level evaluation.  It saves ~1 of ~6 fine-grid
+// passes per lane, but its vector is then taken at a shift that is only ~1e-11 converged and the Simpson Rayleigh
+// quotient -- which weighs the far end of the spectrum heavily -- moves by up to 6e-11 relative; and at warp level the
+// acceptance test has to hold for all 32 lanes, so there was no measurable speed-up.)
 constexpr int PEAK_SNAP = 16;      // a coarsest-level peak within Nl / PEAK_SNAP rows of the middle keeps the middle matching row    // max|z| / |z_k| above which the matching row is moved (see solve_item)
 
 constexpr int FLAG_NOT_CONVERGED = 1, FLAG_BAD_INPUT = 2, FLAG_SIGMA_NOT_MAX = 4;   // = IBS_FLAG_* of include/ibs_b200.h
@@ -401,7 +400,6 @@ struct Sweep {
     double a0e, a0o, a1e, a1o, aDe, aDo;   // sum t' X^2, sum F' X^2, sum g D^2 of the even / odd rows (no dynamic indexing)
     double aEnd;                  // g D^2 of the Dirichlet end point
     double vmax; int jmax;        // largest |x| so far (running scale) and its row
-    int nodes;                    // sign changes of x along the sweep
     bool bad;
     double fsc, cn; int ex;       // writing pass: X = x * fsc, fsc = cn 2^ex (ex follows the rescalings)
 };
@@ -409,7 +407,6 @@ struct Sweep {
 struct SolveOut {                 // what the output pass returns per solve
     double gam, zmax; int jmax; bool bad;
     double xkf, xkb; int Ekf, Ekb;     // the two sweeps at the matching row: value and scale exponent
-    double r, S; int nodes;            // what eval_pass returns (the pass can stand in for an evaluation)
 };
 
 constexpr double C23 = 2.0 / 3.0, C12 = 1.0 / 12.0;
@@ -452,7 +449,6 @@ IBS_HD void out_step(Sweep& sw, const Rec& rc, double th0, double lam, int qq, i
     double xn;
     if (DIR > 0) { xn = fma(sw.w, ia, sw.x); sw.w = fma(-tnew, xn, sw.w); }
     else         { sw.w = fma(sw.tcur, sw.x, sw.w); xn = fma(-sw.w, ia, sw.x); sw.tcur = tnew; }
-    if (!WRITE) sw.nodes += (int)(sign_bit(sw.x) ^ sign_bit(xn));
     sw.x = xn;
     if (WRITE) {
         if (!last && Xw) Xw[row] = norm_value(xn, sw.fsc);
@@ -485,7 +481,7 @@ IBS_HD void out_step(Sweep& sw, const Rec& rc, double th0, double lam, int qq, i
 IBS_HD void sweep_zero(Sweep& sw) {
     sw.E = 0; sw.W1 = sw.W2 = sw.W3 = sw.W4 = 0.0; sw.tcur = 0.0;
     sw.a0e = sw.a0o = sw.a1e = sw.a1o = sw.aDe = sw.aDo = 0.0; sw.aEnd = 0.0;
-    sw.vmax = 0.0; sw.jmax = 0; sw.nodes = 0; sw.bad = false;
+    sw.vmax = 0.0; sw.jmax = 0; sw.bad = false;
 }
 
 // ---- pipelined form of the output-pass step (interior rows: generic stencil, never the last backward step) -----
@@ -497,7 +493,6 @@ IBS_HD void out_chain_tail(Sweep& sw, const OCo& c, int row, double* Xw) {
     double xn;
     if (DIR > 0) { xn = fma(sw.w, c.ia, sw.x); sw.w = fma(-c.t, xn, sw.w); }
     else         { sw.w = fma(sw.tcur, sw.x, sw.w); xn = fma(-sw.w, c.ia, sw.x); sw.tcur = c.t; }
-    if (!WRITE) sw.nodes += (int)(sign_bit(sw.x) ^ sign_bit(xn));
     sw.x = xn;
     if (WRITE) {
         if (Xw) Xw[row] = norm_value(xn, sw.fsc);
@@ -722,9 +717,6 @@ IBS_PASS void out_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL
         const double sX0 = zf2 * (w43 * f.a0o + w23 * f.a0e) + zb2 * (w43 * b.a0o + w23 * b.a0e);
         const double sX1 = zf2 * (w43 * f.a1o + w23 * f.a1e) + zb2 * (w43 * b.a1o + w23 * b.a1e);
         o.gam = lam[q] + (sX0 - 2.0 * sD) / sX1;
-        o.r = b.w * zb - f.w * zf;
-        o.S = zf2 * (f.a1o + f.a1e) + zb2 * (b.a1o + b.a1e);
-        o.nodes = f.nodes + b.nodes;
         const double mf = f.vmax * fabs(zf), mb = b.vmax * fabs(zb);
         o.zmax = fmax(mf, mb);
         o.jmax = (mb > mf) ? b.jmax : f.jmax;
@@ -773,13 +765,13 @@ IBS_HD void fixup_solve(Ctx& ctx, double* X, double* dX, int N, bool zero_X, dou
 
 // ---- bracketed Rayleigh-quotient iteration (per solve; the logic of ibs_solver.cu) -----------------------
 struct Iter {
-    double lam, rho, lo, hi, b1, N1, b2, N2, dprev, dprev2;
+    double lam, rho, lo, hi, b1, N1, b2, N2, dprev;
     int nabove, it;
     bool collapsed, done, conv, warm;
 };
 
 IBS_HD void iter_init(Iter& s, double l0, double Lb, double U, bool frozen) {
-    s.lo = Lb; s.hi = U; s.b1 = s.N1 = s.b2 = s.N2 = 0.0; s.dprev = 1e300; s.dprev2 = 1e300; s.nabove = 0; s.it = 0;
+    s.lo = Lb; s.hi = U; s.b1 = s.N1 = s.b2 = s.N2 = 0.0; s.dprev = 1e300; s.nabove = 0; s.it = 0;
     s.collapsed = false; s.done = frozen; s.conv = frozen;
     s.warm = (l0 > Lb && l0 < U);
     s.lam = s.warm ? l0 : U;
@@ -812,7 +804,7 @@ IBS_HD void iter_update(Iter& s, double r, double S, int nodes, double U, double
             const double q = dl / s.dprev;
             if (dl * q * q <= 0.01 * tol) { s.conv = true; done = true; }
         }
-        s.dprev2 = s.dprev; s.dprev = dl;
+        s.dprev = dl;
     }
     if (!done && s.collapsed) { s.conv = true; done = true; }
     if (!done) {
@@ -854,9 +846,9 @@ template <int SPL>
 struct ColdState {
     Iter it[SPL];
     SolveOut out[SPL];
-    double rho1[SPL], rho2[SPL], rbest[SPL], Kest[SPL];
+    double rho1[SPL], rho2[SPL], rbest[SPL];
     int nev[SPL], flags[SPL];
-    bool fin[SPL], wr[SPL], need[SPL], o1at[SPL];
+    bool fin[SPL], wr[SPL], need[SPL];
 };
 template <int SPL> struct ColdStride { static constexpr int value = (int)((sizeof(ColdState<SPL>) + 7) / 8) | 1; };     // doubles, odd
 
@@ -890,19 +882,16 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
     SolveOut (&out)[SPL] = cs.out;
     double (&rho1)[SPL] = cs.rho1; double (&rho2)[SPL] = cs.rho2;
     double (&rbest)[SPL] = cs.rbest;                    // best eigenvalue estimate of the matrix pencil
-    double (&Kest)[SPL] = cs.Kest;                      // convergence constant e_{n+1} / e_n^2 seen on the previous level
     int (&nev)[SPL] = cs.nev; int (&flags)[SPL] = cs.flags;
     bool (&fin)[SPL] = cs.fin; bool (&wr)[SPL] = cs.wr; bool (&need)[SPL] = cs.need;
-    bool (&o1at)[SPL] = cs.o1at;                        // the solve's last iteration pass was an output pass
     double sh[SPL], r[SPL], S[SPL];                     // sh: the shifts of the next pass
     int nodes[SPL];
-    bool skip_o1 = false;
     double* Xraw[SPL];
     const bool want_out = P.want_X || P.want_dX;
 #pragma unroll
     for (int q = 0; q < SPL; ++q) {
         Xraw[q] = nullptr;
-        rho1[q] = qnan; rho2[q] = qnan; nev[q] = 0; flags[q] = 0; fin[q] = false; wr[q] = false; need[q] = false; o1at[q] = false; rbest[q] = qnan; Kest[q] = 1e300;
+        rho1[q] = qnan; rho2[q] = qnan; nev[q] = 0; flags[q] = 0; fin[q] = false; wr[q] = false; need[q] = false; rbest[q] = qnan;
         iter_init(it[q], qnan, P.Lb, P.U, false);
         sh[q] = it[q].lam;
         if (MODE == MODE_OUT) {          // continue a MODE_ITER run
@@ -918,28 +907,12 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
     bool fix_any = false;
     for (;;) {
         // ---- the streaming pass of this phase: ONE call site per kind of pass
-        // Fine level, once the corrections are small: the output pass stands in for the evaluation (same chains with
-        // reciprocals; it also returns r, S and the node count), so that the pass that confirms convergence is the one
-        // that delivers the eigenfunction sums.
-        bool o1it = false;
-        if (OUT_PASS_AS_EVAL && phase == PH_ITER && lev == 0) {
-            bool near = true;
-#pragma unroll
-            for (int q = 0; q < SPL; ++q)      // predicted (correction ratio)^2 = error of the vector at this shift <~ 1e-10
-                near = near && (it[q].done || (it[q].dprev <= 1e-4 * scale && Kest[q] * it[q].dprev <= 1e-5));
-            o1it = ctx.all(near);
-        }
-        const int kind = (phase == PH_ITER) ? (o1it ? 2 : 1) : (phase == PH_SIGMA) ? 1 : (phase == PH_PEAK) ? 2 :
-                         (phase == PH_O1) ? (skip_o1 ? 0 : 2) : 3;
+        const int kind = (phase == PH_ITER || phase == PH_SIGMA) ? 1 : (phase == PH_PEAK || phase == PH_O1) ? 2 : 3;
         if (kind == 1 || MODE == MODE_ITER) eval_pass<SPL>(ctx, lev, Nl, k, th0, sh, r, S, nodes);
         else if (kind == 2) out_pass<SPL, false>(ctx, lev, Nl, k, th0, sh, out, Xraw);
-        else if (kind == 3) out_pass<SPL, true>(ctx, lev, Nl, k, th0, sh, out, Xraw);
+        else out_pass<SPL, true>(ctx, lev, Nl, k, th0, sh, out, Xraw);
         // ---- what the phase does with it
         if (phase == PH_ITER || phase == PH_SIGMA) {
-            if (o1it) {
-#pragma unroll
-                for (int q = 0; q < SPL; ++q) { r[q] = out[q].r; S[q] = out[q].S; nodes[q] = out[q].nodes; }
-            }
             if (phase == PH_SIGMA) {
 #pragma unroll
                 for (int q = 0; q < SPL; ++q)
@@ -949,10 +922,7 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
             bool alldone = true;
 #pragma unroll
             for (int q = 0; q < SPL; ++q) {
-                if (!it[q].done) {
-                    nev[q] += (1 << MAXLEV) >> lev;     // in units of the coarsest level's share of a fine-grid evaluation
-                    o1at[q] = o1it;
-                }
+                if (!it[q].done) nev[q] += (1 << MAXLEV) >> lev;     // in units of the coarsest level's share of a fine-grid evaluation
                 iter_update(it[q], r[q], S[q], nodes[q], P.U, tol, tol_stag, (lev > 0) ? 1e-7 * scale : tol, lev == 0);
                 alldone &= it[q].done;
                 sh[q] = it[q].lam;
@@ -961,11 +931,7 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
             // ---- this level has converged
             if (lev > 0) {
 #pragma unroll
-                for (int q = 0; q < SPL; ++q) {
-                    rho2[q] = rho1[q]; rho1[q] = (it[q].conv && it[q].rho == it[q].rho) ? it[q].rho : qnan;
-                    // quadratic convergence e_{n+1} = K e_n^2: K from the last two corrections of this level (if it has two)
-                    Kest[q] = (it[q].dprev2 < 1e299 && it[q].dprev2 > 0.0 && it[q].dprev > tol) ? it[q].dprev / (it[q].dprev2 * it[q].dprev2) : 1e300;
-                }
+                for (int q = 0; q < SPL; ++q) { rho2[q] = rho1[q]; rho1[q] = (it[q].conv && it[q].rho == it[q].rho) ? it[q].rho : qnan; }
                 if (MODE != MODE_ITER && lev == P.nlev) {
 #pragma unroll
                     for (int q = 0; q < SPL; ++q) sh[q] = (rho1[q] == rho1[q]) ? rho1[q] : it[q].lam;
@@ -973,18 +939,11 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
                     continue;
                 }
             } else {
-                // the eigenfunction sums of the last pass can be kept if that pass was an output pass of this very solve
-                // at a shift already within ~1e-10 (relative to the gap) of the eigenvalue: its correction contracted by
-                // 1e-5 or is at the rounding floor
-                bool keep = true;
 #pragma unroll
                 for (int q = 0; q < SPL; ++q)
                     if (!fin[q]) {
-                        const bool good = it[q].conv && it[q].rho == it[q].rho;
-                        rbest[q] = good ? it[q].rho : it[q].lam;
-                        const bool ok1 = o1at[q] && good && (it[q].dprev <= tol || it[q].dprev <= 1e-5 * it[q].dprev2);
-                        sh[q] = ok1 ? it[q].lam : rbest[q];            // (it.lam = the shift of the last pass)
-                        keep = keep && ok1;
+                        rbest[q] = (it[q].conv && it[q].rho == it[q].rho) ? it[q].rho : it[q].lam;
+                        sh[q] = rbest[q];
                         if (!it[q].conv) flags[q] |= FLAG_NOT_CONVERGED;
                     }
                 if (MODE == MODE_ITER) {
@@ -992,7 +951,6 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
                     for (int q = 0; q < SPL; ++q) res[q].rho = rbest[q];
                     break;
                 }
-                skip_o1 = ctx.all(keep);
                 phase = PH_O1;
                 continue;
             }
@@ -1006,7 +964,6 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
             const int kp = (jlo + jhi) / 2, km = (Nl - 1) / 2;
             k = clamp_k((kp > km ? kp - km : km - kp) * PEAK_SNAP <= Nl ? km : kp, Nl);
         } else if (phase == PH_O1) {
-            skip_o1 = false;
             bool wr_any = false;
             fix_any = false;
             lowq_any = false; jsel = -1;
