@@ -3,7 +3,10 @@ its forward-difference Jacobian, exactly as the reference's optimiser forms them
 
 ``sims_runner_NCSX.py:313``:  ``f0 = f0 + prefac[-1] * sum(max(gamma_ball - gamma_ball_thresh, 0))``, returned as ``sqrt(f0)``;
 ``sims_runner_NCSX.py:254-261``: ``df0[i] = (f0_i - f0_0) / step_i * 0.5 / sqrt(f0_0)``.
-The true adjoint through the geometry to the boundary DOFs (second half of f3) is not built.
+Second half of f3: ``hf_jacobian`` forms the same Jacobian from ONE scan of the base equilibrium plus the first-order
+change of every surface's maximum growth rate under each perturbed equilibrium (``scan.hellmann_feynman_gamma``: K1 on
+the arg-max field lines + one K4 contraction per degree of freedom, no eigen-solve) instead of ``ndofs + 1`` full scans.
+The perturbed equilibria themselves (VMEC runs) stay outside this package.
 """
 from __future__ import annotations
 
@@ -37,3 +40,13 @@ def fd_jacobian(f0_other, gamma_ball_all, step_arr, thresh: float = GAMMA_BALL_T
     for i in range(1, n):
         df[0, i] = (f[i] - f[0]) / step_arr[i] * 0.5 * 1 / np.sqrt(f[0])
     return f, df
+
+
+def hf_jacobian(f0_other, gamma_base, dgamma, step_arr, thresh: float = GAMMA_BALL_THRESH["NCSX"], prefac: float = PREFAC_BALL):
+    """As ``fd_jacobian``, with the growth rates of the perturbed equilibria predicted to first order:
+    ``gamma_i = gamma_base + dgamma[i - 1]`` (``scan.hellmann_feynman_gamma``).  ``f0_other`` has ``ndofs + 1`` entries
+    (0 = base), ``dgamma`` is ``(ndofs, ns)``."""
+    gamma_base = np.asarray(gamma_base, dtype=np.float64)
+    dgamma = np.asarray(dgamma, dtype=np.float64).reshape(-1, gamma_base.size)
+    gam_all = [gamma_base] + [gamma_base + d for d in dgamma]
+    return fd_jacobian(f0_other, gam_all, step_arr, thresh, prefac)

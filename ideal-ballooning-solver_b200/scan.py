@@ -282,6 +282,55 @@ def ball_scan(st: SurfaceTables, theta=None, mpol: Optional[int] = None, ntor: O
                           X=sol.X.cpu().numpy(), refine=ref)
 
 
+def _gcf_exact(geo, theta0: torch.Tensor):
+    """``g, c, f`` (``utils.py:1560-1562``) of one solve per field line of ``geo`` at ``theta0`` (``ball_scan.py:267-268``),
+    as torch expressions in the reference's operation order.  ``geo.base`` is ``(nline, 8, N)`` flattened."""
+    b = geo.base.reshape(-1, engine.NBASE, geo.base.shape[-1])
+    B, gp = b[:, engine.BASE_NAMES.index("bmag")], b[:, engine.BASE_NAMES.index("gradpar_theta_pest")].abs()
+    t0 = theta0.reshape(-1, 1)
+    cv = b[:, engine.BASE_NAMES.index("cvdrift")] + t0 * b[:, engine.BASE_NAMES.index("cvdrift0")]
+    gd = (b[:, engine.BASE_NAMES.index("gds2")] + 2 * t0 * b[:, engine.BASE_NAMES.index("gds21")]
+          + t0 ** 2 * b[:, engine.BASE_NAMES.index("gds22")])
+    dP = geo.dPdrho.reshape(-1, 1)
+    return gp * gd / B, -1 * dP * cv * 1 / (gp * B), gd / B ** 2 * 1 / (gp * B)
+
+
+@dataclasses.dataclass
+class GammaSensitivity:
+    gamma: np.ndarray          # (ns,) growth rate of the base equilibrium at (alpha*, theta0*)
+    dgamma: np.ndarray         # (ndof, ns) first-order change for every perturbed equilibrium
+    X: np.ndarray              # (ns, nl) eigenfunction of the base equilibrium
+
+
+def hellmann_feynman_gamma(tables0: engine.DeviceTables, tables_pert, alpha_star, theta0_star, theta) -> GammaSensitivity:
+    """SURVEY.md section 8 row f3 (second half): the change of every surface's maximum growth rate under perturbed
+    equilibria WITHOUT re-scanning them.  The reference re-runs the whole scan for each of the ``ndofs + 1`` equilibria
+    of a finite-difference Jacobian (``sims_runner_NCSX.py:245-262``); to first order the change of the maximum is the
+    change at fixed ``(alpha*, theta0*)`` (the maximum is stationary in both) and, at fixed eigenfunction, the
+    Hellmann-Feynman contraction the reference itself uses for its (alpha, theta0) gradients (``utils.py:1676-1680``):
+
+        d gam = [ int dc X^2 - int dg dX^2 - gam int df X^2 ] / int f X^2,   (dg, dc, df) = (g, c, f)_pert - (g, c, f)_base
+
+    with the perturbed coefficients from K1 on the SAME field lines.  Cost per degree of freedom: ``ns`` field lines of
+    geometry + one K4 contraction, instead of a full (alpha, theta0) scan + refinement."""
+    dev = tables0.tab_mn.device
+    theta_np = theta.cpu().numpy() if isinstance(theta, torch.Tensor) else np.asarray(theta, dtype=np.float64)
+    h = engine.grid_spacing(theta_np)
+    a = torch.as_tensor(np.asarray(alpha_star, dtype=np.float64)).reshape(-1, 1).to(dev)
+    t0 = torch.as_tensor(np.asarray(theta0_star, dtype=np.float64)).reshape(-1).to(dev)
+    geo0 = engine.geometry_batch(tables0, a, theta_np)
+    sol = engine.solve_base_batch(geo0.base, geo0.dPdrho, t0, h, nth0=1, want_dX=True, want_matrix=False)
+    g0, c0, f0 = _gcf_exact(geo0, t0)
+    dg, dc, df = [], [], []
+    for tp in tables_pert:
+        gi, ci, fi = _gcf_exact(engine.geometry_batch(tp, a, theta_np), t0)
+        dg.append(gi - g0); dc.append(ci - c0); df.append(fi - f0)
+    if not dg:
+        return GammaSensitivity(sol.lam.cpu().numpy(), np.zeros((0, t0.numel())), sol.X.cpu().numpy())
+    grad = engine.adjoint_batch(sol.lam, sol.X, sol.dX, f0, torch.stack(dg, 1), torch.stack(dc, 1), torch.stack(df, 1))
+    return GammaSensitivity(sol.lam.cpu().numpy(), grad.t().contiguous().cpu().numpy(), sol.X.cpu().numpy())
+
+
 def save_results(path: str, dof_idx: int, iter0: int, result: BallScanResult) -> None:
     """Append one row per call to ``ball_gam<dof>.npy``, ``ball_theta0<dof>.npy``, ``ball_alpha<dof>.npy`` with the
     reference's semantics (``ball_scan.py:359-384``): at ``iter0 == 0`` the placeholder first element written by

@@ -54,3 +54,36 @@ def test_refine_batches_all_surfaces(cuda_lib, golden):
     assert r.nbatches <= int(r.nfev.max()) + 2 and int(r.nfev.sum()) > 3 * r.nbatches
     assert np.all(res.gamma >= res.gamma_coarse.reshape(64, -1).max(axis=1) - 1e-12)
     assert np.all(np.isfinite(res.gamma)) and res.X.shape == (64, 513)
+
+
+def test_hellmann_feynman_gamma_predicts_perturbed_growth_rates(cuda_lib):
+    """f3, second half: the first-order change of each surface's growth rate under perturbed equilibria from one
+    eigen-solve per surface (K1 on the same field lines + K4), against actually re-solving the perturbed problems."""
+    import dataclasses
+    import torch
+    from ideal_ballooning_solver_b200 import engine, scan, synthetic, tables, penalty
+    st = tables.RadialSplines(synthetic.make_equilibrium("ncsx", seed=11)).evaluate(np.linspace(0.55, 0.9, 6))
+    theta = np.linspace(-3 * np.pi, 3 * np.pi, 513)
+    rng = np.random.default_rng(5)
+    a_star, t_star = rng.uniform(0.2, 2.5, st.ns), rng.uniform(0.0, 1.2, st.ns)
+    eps = 1.0e-5
+    perts = []
+    for k in range(3):                      # smooth relative perturbations of the shape / field tables
+        w_mn = 1.0 + eps * rng.standard_normal(st.tab_mn.shape[1:])[None] * np.exp(-0.3 * np.arange(st.tab_mn.shape[2]))[None, None]
+        w_nq = 1.0 + eps * rng.standard_normal(st.tab_nyq.shape[1:])[None] * np.exp(-0.3 * np.arange(st.tab_nyq.shape[2]))[None, None]
+        perts.append(dataclasses.replace(st, tab_mn=st.tab_mn * w_mn, tab_nyq=st.tab_nyq * w_nq))
+    dt0 = engine.DeviceTables.from_host(st)
+    dts = [engine.DeviceTables.from_host(p) for p in perts]
+    sens = scan.hellmann_feynman_gamma(dt0, dts, a_star, t_star, theta)
+    assert sens.dgamma.shape == (3, st.ns) and np.all(np.isfinite(sens.dgamma))
+    h = engine.grid_spacing(theta)
+    a = torch.from_numpy(a_star[:, None].copy()).cuda()
+    t0 = torch.from_numpy(t_star.copy()).cuda()
+    for k, dtp in enumerate(dts):
+        geo = engine.geometry_batch(dtp, a, theta)
+        lam_p = engine.solve_base_batch(geo.base, geo.dPdrho, t0, h, nth0=1, want_X=False, want_dX=False, want_matrix=False).lam.cpu().numpy()
+        actual = lam_p - sens.gamma
+        # first order in eps: the remainder is O(eps^2) relative to the change itself (plus rounding of the difference)
+        np.testing.assert_allclose(sens.dgamma[k], actual, rtol=2e-3, atol=1e-12 * np.abs(sens.gamma).max() + 1e-14)
+    f, df = penalty.hf_jacobian([0.3] * 4, sens.gamma, sens.dgamma, np.array([0.0, eps, eps, eps]), thresh=float(np.median(sens.gamma)))
+    assert np.all(np.isfinite(df)) and df.shape == (1, 4)

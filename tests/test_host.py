@@ -142,3 +142,15 @@ def test_ballooning_penalty_matches_reference_formula():
     f, df = penalty.fd_jacobian([0.25, 0.26, 0.24], gams, np.array([0.0, 1e-3, 2e-3]))
     assert df.shape == (1, 3) and df[0, 0] == 0
     np.testing.assert_allclose(df[0, 1], (f[1] - f[0]) / 1e-3 * 0.5 / np.sqrt(f[0]))
+
+
+def test_hf_jacobian_is_fd_jacobian_on_predicted_growth_rates():
+    from ideal_ballooning_solver_b200 import penalty
+    gam0 = np.array([-1e-3, 2e-4, 5e-4, -3e-4])
+    dgam = np.array([[1e-5, -2e-5, 3e-5, 4e-4], [0.0, 1e-5, -1e-3, 0.0]])
+    steps = np.array([0.0, 1e-3, 2e-3])
+    f, df = penalty.hf_jacobian([0.25, 0.26, 0.24], gam0, dgam, steps)
+    f2, df2 = penalty.fd_jacobian([0.25, 0.26, 0.24], [gam0, gam0 + dgam[0], gam0 + dgam[1]], steps)
+    assert np.array_equal(f, f2) and np.array_equal(df, df2)
+    # the threshold kink is honoured: surface 3 crosses the threshold under the first perturbation
+    assert f[1] - f[0] > 0.01 + penalty.PREFAC_BALL * (1e-5 - 2e-5 + 3e-5)
