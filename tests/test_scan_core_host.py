@@ -83,3 +83,22 @@ def test_lane_code_off_centre_modes(harness):
         X = X * np.sign(X[np.argmax(np.abs(X))])
         assert abs(R["lam"][0, t] - gam) <= LAM_RTOL * abs(gam)
         np.testing.assert_allclose(R["X"][t], X, rtol=0, atol=X_ATOL)
+
+
+@pytest.mark.parametrize("n", [65, 129, 257])
+def test_lane_code_small_grids(harness, n):
+    """N = 65 has no coarse level (cold start on the fine grid), 129 one, 257 two."""
+    from oracle import ballooning_oracle as bo
+    shc, lib = harness
+    theta = np.linspace(-2 * np.pi, 2 * np.pi, n)
+    th0 = np.linspace(0.0, 1.0, 4)
+    base, dP = s_alpha_base(0.8, 0.9, theta)
+    R = shc.host_scan_solve(lib, base[None], np.array([dP]), th0[None], theta[1] - theta[0])
+    assert lib.scan_host_num_levels(n) == {65: 0, 129: 1, 257: 2}[n]
+    assert np.all((R["info"] >> 16) == 0)
+    for t, t0 in enumerate(th0):
+        gam, X, dX, *_ = bo.gamma_ball_full(dP, theta, base[0], base[1], base[2] + t0 * base[3],
+                                            base[4] + 2 * t0 * base[5] + t0 ** 2 * base[6], method="lambda_max")
+        X = X * np.sign(X[np.argmax(np.abs(X))])
+        assert abs(R["lam"][0, t] - gam) <= LAM_RTOL * abs(gam)
+        np.testing.assert_allclose(R["X"][t], X, rtol=0, atol=X_ATOL)

@@ -177,3 +177,23 @@ def test_scan_kernel_two_kernel_form(cuda_lib, golden, name):
     np.testing.assert_allclose(two.lam.cpu().numpy(), one.lam.cpu().numpy(), rtol=LAM_RTOL, atol=0)
     np.testing.assert_allclose(two.X.cpu().numpy(), one.X.cpu().numpy(), rtol=0, atol=X_ATOL)
     np.testing.assert_allclose(two.dX.cpu().numpy(), one.dX.cpu().numpy(), rtol=0, atol=10 * X_ATOL * max(1.0, float(one.dX.abs().max())))
+
+
+@pytest.mark.parametrize("n", [65, 129, 257, 969])
+def test_scan_kernel_small_and_odd_grids(cuda_lib, n):
+    """Grids with 0, 1, 2 coarse levels and one whose coarse levels have an even number of points (969 = 8 * 121 + 1)."""
+    import torch
+    from ideal_ballooning_solver_b200 import engine
+    theta = np.linspace(-2 * np.pi, 2 * np.pi, n)
+    h = engine.grid_spacing(theta)
+    cases = [(0.8, 0.9), (1.1, 0.5)]
+    bases, dPs = zip(*[s_alpha_base(s, a, theta) for s, a in cases])
+    t0 = np.linspace(0.0, 1.2, 33)                        # two groups of lanes, the second with one active lane
+    base, dP = torch.from_numpy(np.array(bases)).cuda(), torch.from_numpy(np.array(dPs)).cuda()
+    th0 = torch.from_numpy(np.tile(t0, len(cases))).cuda()
+    new = _solve(base, dP, th0, h, len(t0), True)
+    old = _solve(base, dP, th0, h, len(t0), False)
+    assert np.all(new.flags.cpu().numpy() == 0)
+    np.testing.assert_allclose(new.lam.cpu().numpy(), old.lam.cpu().numpy(), rtol=LAM_RTOL, atol=0)
+    np.testing.assert_allclose(new.X.cpu().numpy(), old.X.cpu().numpy(), rtol=0, atol=X_ATOL)
+    np.testing.assert_allclose(new.dX.cpu().numpy(), old.dX.cpu().numpy(), rtol=0, atol=10 * X_ATOL * max(1.0, float(old.dX.abs().max())))
