@@ -305,42 +305,41 @@ static int scan_launch(const ScanParams& sp, cudaStream_t stream) {
     return IBS_OK;
 }
 
-int scan_solve_dispatch(const SolveParams& p, cudaStream_t stream) {
+// One launch set (prep + solver) for the lines [l0, l0 + nline) of the batch p
+static int scan_solve_lines(const SolveParams& p, int l0, int nline, int spl, bool two, cudaStream_t stream) {
     const int N = p.N;
-    const int nline = p.nsolve / p.nth0;
     const int nlev = num_levels(N);
     const int rows_total = level_offset(N, nlev + 1);
-    int spl = 1;        // two solves per lane (IBS_SCAN_SPL=2) halve the shared-memory traffic but spill at 255 registers: slower
-    if (const char* e = std::getenv("IBS_SCAN_SPL")) { const int v = std::atoi(e); if (v == 1 || v == 2) spl = v; }
-    keep_pool_cached();
+    const size_t v0 = (size_t)l0 * p.nth0, nsolve = (size_t)nline * p.nth0;
     const size_t poly_bytes = (size_t)nline * rows_total * REC * sizeof(double);
     const size_t bounds_off = (poly_bytes + 255) & ~(size_t)255;
     const size_t counter_off = bounds_off + (((size_t)nline * 2 * sizeof(double) + 255) & ~(size_t)255);
-    // two-kernel form (IBS_SCAN_TWO=1): iteration kernel (fewer registers, more resident warps) + output kernel
-    bool two = false;
-    if (const char* e = std::getenv("IBS_SCAN_TWO")) two = std::atoi(e) != 0;
     const size_t hand_off = counter_off + 256;
-    const size_t hand_bytes = two ? ((((size_t)p.nsolve * (sizeof(double) + sizeof(int))) + 255) & ~(size_t)255) : 0;
+    const size_t hand_bytes = two ? (((nsolve * (sizeof(double) + sizeof(int))) + 255) & ~(size_t)255) : 0;
     const size_t xs_off = hand_off + hand_bytes;
-    const size_t xs_bytes = (p.dX_out && !p.X_out) ? (size_t)p.nsolve * N * sizeof(double) : 0;      // X is the scratch dX is formed from
+    const size_t xs_bytes = (p.dX_out && !p.X_out) ? nsolve * N * sizeof(double) : 0;      // X is the scratch dX is formed from
     char* ws = nullptr;
     IBS_CUDA_CHECK(cudaMallocAsync((void**)&ws, xs_off + xs_bytes + 256, stream));
     int rc = IBS_OK;
     ScanParams sp;
     sp.poly = (double*)ws; sp.bounds = (double*)(ws + bounds_off); sp.counter = (unsigned*)(ws + counter_off);
-    sp.theta0 = p.theta0; sp.sigma = p.sigma;
+    sp.theta0 = p.theta0 + v0; sp.sigma = p.sigma ? p.sigma + v0 : nullptr;
     sp.nline = nline; sp.nth0 = p.nth0; sp.N = N; sp.nlev = nlev; sp.rows_total = rows_total;
     sp.groups = (p.nth0 + 32 * spl - 1) / (32 * spl);
     sp.nitems = nline * sp.groups;
     sp.h = p.h;
-    sp.lam_out = p.lam_out; sp.lam_matrix_out = p.lam_matrix_out; sp.X_out = p.X_out; sp.dX_out = p.dX_out; sp.info_out = p.info_out;
-    sp.X_rows = p.X_out ? p.X_out : (xs_bytes ? (double*)(ws + xs_off) : nullptr);
+    sp.lam_out = p.lam_out + v0;
+    sp.lam_matrix_out = p.lam_matrix_out ? p.lam_matrix_out + v0 : nullptr;
+    sp.X_out = p.X_out ? p.X_out + v0 * N : nullptr;
+    sp.dX_out = p.dX_out ? p.dX_out + v0 * N : nullptr;
+    sp.info_out = p.info_out ? p.info_out + v0 : nullptr;
+    sp.X_rows = sp.X_out ? sp.X_out : (xs_bytes ? (double*)(ws + xs_off) : nullptr);
     sp.shift_ws = two ? (double*)(ws + hand_off) : nullptr;
-    sp.info_ws = two ? (int*)(ws + hand_off + (size_t)p.nsolve * sizeof(double)) : nullptr;
+    sp.info_ws = two ? (int*)(ws + hand_off + nsolve * sizeof(double)) : nullptr;
     if (cudaMemsetAsync(sp.counter, 0, 2 * sizeof(unsigned), stream) != cudaSuccess) rc = IBS_ERR_CUDA;
     if (rc == IBS_OK) {
-        scan_prep_kernel<<<nline, PREP_T, 0, stream>>>(p.base, p.dPdrho, p.theta0, p.nth0, N, p.h * p.h, nlev, rows_total,
-                                                       (double*)ws, (double*)(ws + bounds_off));
+        scan_prep_kernel<<<nline, PREP_T, 0, stream>>>(p.base + (size_t)l0 * IBS_NBASE * N, p.dPdrho + l0, sp.theta0, p.nth0, N, p.h * p.h, nlev,
+                                                       rows_total, (double*)ws, (double*)(ws + bounds_off));
         if (cudaGetLastError() != cudaSuccess) { set_error("scan_prep_kernel launch failed"); rc = IBS_ERR_CUDA; }
     }
     if (rc == IBS_OK) {
@@ -352,6 +351,27 @@ int scan_solve_dispatch(const SolveParams& p, cudaStream_t stream) {
         }
     }
     cudaFreeAsync(ws, stream);
+    return rc;
+}
+
+int scan_solve_dispatch(const SolveParams& p, cudaStream_t stream) {
+    const int nline = p.nsolve / p.nth0;
+    int spl = 1;        // two solves per lane (IBS_SCAN_SPL=2) halve the shared-memory traffic but spill at 255 registers: slower
+    if (const char* e = std::getenv("IBS_SCAN_SPL")) { const int v = std::atoi(e); if (v == 1 || v == 2) spl = v; }
+    // two-kernel form (IBS_SCAN_TWO=1): iteration kernel (fewer registers, more resident warps) + output kernel
+    bool two = false;
+    if (const char* e = std::getenv("IBS_SCAN_TWO")) two = std::atoi(e) != 0;
+    keep_pool_cached();
+    // The coefficient records take ~95 KB per field line (N = 1025): very large batches are processed in chunks of lines so
+    // that the stream-ordered workspace stays below IBS_SCAN_WS_MB (default 8 GB; the chunks are still >> one round of warps).
+    size_t ws_mb = 8192;
+    if (const char* e = std::getenv("IBS_SCAN_WS_MB")) { const long v = std::atol(e); if (v >= 1) ws_mb = (size_t)v; }
+    const size_t per_line = (size_t)level_offset(p.N, num_levels(p.N) + 1) * REC * sizeof(double) + 64;
+    long long chunk = (long long)((ws_mb << 20) / per_line);
+    if (chunk < 1) chunk = 1;
+    int rc = IBS_OK;
+    for (long long l0 = 0; l0 < nline && rc == IBS_OK; l0 += chunk)
+        rc = scan_solve_lines(p, (int)l0, (int)((nline - l0 < chunk) ? (nline - l0) : chunk), spl, two, stream);
     return rc;
 }
 

@@ -197,3 +197,26 @@ def test_scan_kernel_small_and_odd_grids(cuda_lib, n):
     np.testing.assert_allclose(new.lam.cpu().numpy(), old.lam.cpu().numpy(), rtol=LAM_RTOL, atol=0)
     np.testing.assert_allclose(new.X.cpu().numpy(), old.X.cpu().numpy(), rtol=0, atol=X_ATOL)
     np.testing.assert_allclose(new.dX.cpu().numpy(), old.dX.cpu().numpy(), rtol=0, atol=10 * X_ATOL * max(1.0, float(old.dX.abs().max())))
+
+
+def test_scan_kernel_chunked_workspace(cuda_lib, golden):
+    """IBS_SCAN_WS_MB bounds the coefficient workspace: the lines are then processed in chunks (here 2 lines per chunk),
+    bit-identical to one launch."""
+    import torch
+    from ideal_ballooning_solver_b200 import engine
+    D = golden("synthetic_ncsx")
+    theta = D["theta"]
+    h = engine.grid_spacing(theta)
+    fb = fixture_base(D)
+    ns, na = fb.shape[:2]
+    base, dP = torch.from_numpy(fb).cuda(), torch.from_numpy(D["dPdrho"]).cuda()
+    th0 = torch.from_numpy(np.tile(np.linspace(0.0, 1.4, 9), ns * na)).cuda()
+    sigma = torch.linspace(-1.0, 1.0, th0.numel(), dtype=torch.float64)
+    one = _solve(base, dP, th0, h, 9, True, sigma=sigma)
+    os.environ["IBS_SCAN_WS_MB"] = "1"
+    try:
+        many = _solve(base, dP, th0, h, 9, True, sigma=sigma)
+    finally:
+        os.environ.pop("IBS_SCAN_WS_MB", None)
+    assert torch.equal(one.lam, many.lam) and torch.equal(one.X, many.X) and torch.equal(one.dX, many.dX)
+    assert torch.equal(one.info, many.info) and torch.equal(one.lam_matrix, many.lam_matrix)
