@@ -25,7 +25,10 @@ constexpr int SC_NSTAGE = IBS_SCAN_NSTAGE;         // pipeline stages per warp
 constexpr int SC_TILE = TR * REC;                  // doubles per tile (1536 B)
 constexpr int SC_STAGE = 2 * SC_TILE;              // forward + backward tile
 constexpr int SC_RING = SC_NSTAGE * SC_STAGE;      // doubles per warp (9 KB with 3 stages)
-constexpr int SC_WARPS = 4;                        // warps per CTA (they never synchronise with each other)
+#ifndef IBS_SCAN_WARPS
+#define IBS_SCAN_WARPS 4
+#endif
+constexpr int SC_WARPS = IBS_SCAN_WARPS;           // warps per CTA (they never synchronise with each other)
 #ifndef IBS_SCAN_CTAS1
 #define IBS_SCAN_CTAS1 2      // CTAs per SM the SPL = 1 kernel is compiled for (register cap 65536 / (128 * CTAS))
 #endif
@@ -132,7 +135,12 @@ struct DevCtx {
 #define IBS_SCAN_CTAS_ITER 3     // CTAs per SM the iteration-only kernel (two-kernel form) is compiled for
 #endif
 template <int SPL, int MODE>
-__global__ void __launch_bounds__(SC_WARPS * 32, (MODE == MODE_ITER) ? IBS_SCAN_CTAS_ITER : ((SPL == 1) ? IBS_SCAN_CTAS1 : 2))
+__global__ void
+#ifdef IBS_SCAN_MAXNREG
+__maxnreg__(IBS_SCAN_MAXNREG)          // tuning builds: explicit register cap (cannot be combined with __launch_bounds__)
+#else
+__launch_bounds__(SC_WARPS * 32, (MODE == MODE_ITER) ? IBS_SCAN_CTAS_ITER : ((SPL == 1) ? IBS_SCAN_CTAS1 : 2))
+#endif
 scan_solve_kernel(const ScanParams p) {
     extern __shared__ __align__(128) double sc_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
