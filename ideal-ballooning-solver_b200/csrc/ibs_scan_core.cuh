@@ -802,7 +802,7 @@ IBS_HD void iter_update(Iter& s, double r, double S, int nodes, double U, double
         // quadratic convergence: the error of rho is ~ dl^3 / dprev^2 once two consecutive corrections contract
         if (predictive && !done && dl < 1e-3 * s.dprev && s.dprev < 1e-2 * fmax(fabs(U), 1e-3)) {
             const double q = dl / s.dprev;
-            if (dl * q * q <= 0.01 * tol) { s.conv = true; done = true; }
+            if (dl * q * q <= 1.0 * tol) { s.conv = true; done = true; }
         }
         s.dprev = dl;
     }
@@ -869,6 +869,27 @@ enum { PH_ITER = 0, PH_PEAK = 1, PH_O1 = 2, PH_O2 = 3, PH_SIGMA = 4 };
 // res[].rho / .info of a MODE_ITER run.
 enum { MODE_FULL = 0, MODE_ITER = 1, MODE_OUT = 2 };
 
+// The output passes need about twice the registers of the iteration pass, so with two solves per lane they are run one
+// solve at a time (the iteration keeps both in flight: twice the instruction-level parallelism, half the record loads).
+template <int SPL, bool WRITE, class Ctx>
+IBS_HD void out_pass_each(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL], const double (&lam)[SPL],
+                          SolveOut (&out)[SPL], double* const (&Xw)[SPL]) {
+    if (SPL == 1) {
+        out_pass<SPL, WRITE>(ctx, lev, Nl, k, th0, lam, out, Xw);
+    } else {
+#pragma unroll 1
+        for (int q = 0; q < SPL; ++q) {
+            const double th1[1] = {q ? th0[SPL - 1] : th0[0]};
+            const double lam1[1] = {q ? lam[SPL - 1] : lam[0]};
+            double* const Xw1[1] = {q ? Xw[SPL - 1] : Xw[0]};
+            SolveOut o1[1];
+            if (WRITE) o1[0] = out[q];
+            out_pass<1, WRITE>(ctx, lev, Nl, k, th1, lam1, o1, Xw1);
+            if (!WRITE) out[q] = o1[0];
+        }
+    }
+}
+
 template <int SPL, int MODE, class Ctx>
 IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL], const bool (&act)[SPL], const double (&sigma)[SPL],
                        const bool has_sigma, double* const (&Xrow)[SPL], double* const (&dXrow)[SPL], ItemResult (&res)[SPL],
@@ -909,8 +930,8 @@ IBS_HD void solve_item(Ctx& ctx, const ItemProblem& P, const double (&th0)[SPL],
         // ---- the streaming pass of this phase: ONE call site per kind of pass
         const int kind = (phase == PH_ITER || phase == PH_SIGMA) ? 1 : (phase == PH_PEAK || phase == PH_O1) ? 2 : 3;
         if (kind == 1 || MODE == MODE_ITER) eval_pass<SPL>(ctx, lev, Nl, k, th0, sh, r, S, nodes);
-        else if (kind == 2) out_pass<SPL, false>(ctx, lev, Nl, k, th0, sh, out, Xraw);
-        else out_pass<SPL, true>(ctx, lev, Nl, k, th0, sh, out, Xraw);
+        else if (kind == 2) out_pass_each<SPL, false>(ctx, lev, Nl, k, th0, sh, out, Xraw);
+        else out_pass_each<SPL, true>(ctx, lev, Nl, k, th0, sh, out, Xraw);
         // ---- what the phase does with it
         if (phase == PH_ITER || phase == PH_SIGMA) {
             if (phase == PH_SIGMA) {
