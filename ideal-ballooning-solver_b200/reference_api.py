@@ -142,3 +142,55 @@ def obj_w_grad(x0, vs, rho_val, theta, vguess00=None, sigma00=0.42):
     if int(info[0].item()) >> 16:
         raise RuntimeError("obj_w_grad: eigen-solve failed (flags %d)" % (int(info[0].item()) >> 16))
     return float(val[0].item()), grad[0].cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# f4 (part): finite-difference helpers of the curvature penalty (host-side numpy in the reference as well)
+# ---------------------------------------------------------------------------------------------------------
+def _fd_layout(arr, ch):
+    """Differencing axis last; 1-D inputs become (1, n) along a surface ('l') and (n, 1) across surfaces ('r'), which is
+    also the shape the reference returns for them (``utils.py:1745-1779``)."""
+    a = np.asarray(arr, dtype=np.float64)
+    if a.ndim == 1:
+        a = a[None, :] if ch == "l" else a[:, None]
+    if a.ndim != 2 or ch not in ("l", "r"):
+        raise ValueError("derm/dermv take 1-D or 2-D arrays and ch in {'l', 'r'}")
+    return (a, 1) if ch == "l" else (a.T, 0)
+
+
+def derm(arr, ch, par="e"):
+    """``derm`` (``utils.py:1737-1807``): un-normalised central difference ``a[i+1] - a[i-1]`` along (``'l'``) or across
+    (``'r'``) the flux surfaces; the ends are ``2 (a[1] - a[0])``, ``2 (a[-1] - a[-2])``, or zero along a surface for an
+    even-parity array."""
+    a, axis = _fd_layout(arr, ch)
+    out = np.zeros_like(a)
+    out[:, 1:-1] = np.diff(a[:, :-1], axis=1) + np.diff(a[:, 1:], axis=1)
+    if not (ch == "l" and par == "e"):
+        out[:, 0] = 2 * (a[:, 1] - a[:, 0])
+        out[:, -1] = 2 * (a[:, -1] - a[:, -2])
+    return out if axis == 1 else np.ascontiguousarray(out.T)
+
+
+def dermv(arr, brr, ch, par="e"):
+    """``dermv`` (``utils.py:1810-1943``): derivative of ``arr`` with respect to the non-uniform ``brr`` (weighted
+    three-point formula inside; one-sided at the ends: second order for a 1-D odd-parity array along a surface, first
+    order otherwise, zero for even parity along a surface).  A 1-D array with ``ch='r'`` raises: the reference stops in
+    the debugger there (``utils.py:1866``)."""
+    one_d = np.ndim(arr) == 1
+    if one_d and ch != "l":
+        raise NotImplementedError("dermv(1-D, 'r'): the reference enters pdb.set_trace() here (utils.py:1866)")
+    a, axis = _fd_layout(arr, ch)
+    b, _ = _fd_layout(brr, ch)
+    out = np.zeros_like(a)
+    h1 = b[:, 2:] - b[:, 1:-1]
+    h0 = b[:, 1:-1] - b[:, :-2]
+    out[:, 1:-1] = (a[:, 2:] / h1 ** 2 + a[:, 1:-1] * (1 / h0 ** 2 - 1 / h1 ** 2) - a[:, :-2] / h0 ** 2) / (1 / h1 + 1 / h0)
+    if ch == "l" and par == "e":
+        pass
+    elif one_d:
+        out[:, 0] = (4 * a[:, 1] - 3 * a[:, 0] - a[:, 2]) / (2 * (b[:, 1] - b[:, 0]))
+        out[:, -1] = (-4 * a[:, -2] + 3 * a[:, -1] + a[:, -3]) / (2 * (b[:, -1] - b[:, -2]))
+    else:
+        out[:, 0] = 2 * (a[:, 1] - a[:, 0]) / (2 * (b[:, 1] - b[:, 0]))
+        out[:, -1] = 2 * (a[:, -1] - a[:, -2]) / (2 * (b[:, -1] - b[:, -2]))
+    return out if axis == 1 else np.ascontiguousarray(out.T)

@@ -359,3 +359,52 @@ def check_ball(shat_n, alpha_n, theta0, span=61, ntheta=1601):
         psi_prime = psi_prime + c1[ig] * psi[ig]
         psi[ig + 1] = (g1[ig + 1] * psi[ig] + psi_prime) * g2[ig + 1]
     return int(np.any(psi[1:-1] * psi[2:] <= 0))
+
+
+# ---------------------------------------------------------------------------------------
+# f4 (part): the finite-difference helpers of the curvature penalty (utils.py:1737-1943)
+# ---------------------------------------------------------------------------------------
+def derm(arr, ch, par="e"):
+    """Restatement of ``derm`` (``utils.py:1737-1807``): un-normalised central differences ``a[i+1] - a[i-1]`` along
+    (``ch='l'``) or across (``ch='r'``) flux surfaces; end points ``2 (a[1] - a[0])`` / ``2 (a[-1] - a[-2])`` -- or 0 along
+    a surface when the input has even parity.  Shapes as the reference returns them: a 1-D input comes back as
+    ``(1, n)`` for ``'l'`` and ``(n, 1)`` for ``'r'``."""
+    a = np.asarray(arr, dtype=float)
+    if a.ndim == 1:
+        a = a.reshape(1, -1) if ch == "l" else a.reshape(-1, 1)
+    axis = 1 if ch == "l" else 0
+    a = np.moveaxis(a, axis, -1)
+    d = np.zeros_like(a)
+    d[..., 1:-1] = (a[..., 1:-1] - a[..., :-2]) + (a[..., 2:] - a[..., 1:-1])      # np.diff + np.diff, as the reference adds them
+    if not (ch == "l" and par == "e"):
+        d[..., 0] = 2 * (a[..., 1] - a[..., 0])
+        d[..., -1] = 2 * (a[..., -1] - a[..., -2])
+    return np.moveaxis(d, -1, axis)
+
+
+def dermv(arr, brr, ch, par="e"):
+    """Restatement of ``dermv`` (``utils.py:1810-1943``): derivative of ``arr`` with respect to the non-uniformly spaced
+    ``brr``; interior ``(a[i+1]/h1^2 + a[i] (1/h0^2 - 1/h1^2) - a[i-1]/h0^2) / (1/h1 + 1/h0)``; end points one-sided
+    (second order for a 1-D odd-parity array along a surface, first order otherwise; 0 for even parity along a
+    surface).  The reference's 1-D ``'r'`` branch stops in ``pdb.set_trace()`` (``utils.py:1866``) and is not restated."""
+    a, b = np.asarray(arr, dtype=float), np.asarray(brr, dtype=float)
+    one_d = a.ndim == 1
+    if one_d:
+        if ch != "l":
+            raise NotImplementedError("dermv(1-D, 'r') enters the debugger in the reference (utils.py:1866)")
+        a, b = a.reshape(1, -1), b.reshape(1, -1)
+    axis = 1 if ch == "l" else 0
+    a, b = np.moveaxis(a, axis, -1), np.moveaxis(b, axis, -1)
+    d = np.zeros_like(a)
+    h1 = b[..., 2:] - b[..., 1:-1]
+    h0 = b[..., 1:-1] - b[..., :-2]
+    d[..., 1:-1] = (a[..., 2:] / h1 ** 2 + a[..., 1:-1] * (1 / h0 ** 2 - 1 / h1 ** 2) - a[..., :-2] / h0 ** 2) / (1 / h1 + 1 / h0)
+    if ch == "l" and par == "e":
+        pass                                                                      # even parity: zero slope at both ends
+    elif one_d:
+        d[..., 0] = (4 * a[..., 1] - 3 * a[..., 0] - a[..., 2]) / (2 * (b[..., 1] - b[..., 0]))
+        d[..., -1] = (-4 * a[..., -2] + 3 * a[..., -1] + a[..., -3]) / (2 * (b[..., -1] - b[..., -2]))
+    else:
+        d[..., 0] = 2 * (a[..., 1] - a[..., 0]) / (2 * (b[..., 1] - b[..., 0]))
+        d[..., -1] = 2 * (a[..., -1] - a[..., -2]) / (2 * (b[..., -1] - b[..., -2]))
+    return np.moveaxis(d, -1, axis)

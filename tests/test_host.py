@@ -154,3 +154,24 @@ def test_hf_jacobian_is_fd_jacobian_on_predicted_growth_rates():
     assert np.array_equal(f, f2) and np.array_equal(df, df2)
     # the threshold kink is honoured: surface 3 crosses the threshold under the first perturbation
     assert f[1] - f[0] > 0.01 + penalty.PREFAC_BALL * (1e-5 - 2e-5 + 3e-5)
+
+
+def test_derm_dermv_facade_matches_reference_golden(golden):
+    """The host facade's derm / dermv (reference_api.py) against the reference's own outputs: bit-exact."""
+    from ideal_ballooning_solver_b200 import reference_api as ra
+    G = golden("derm")
+    n = 0
+    for key in G.files:
+        if not key.startswith("derm"):
+            continue
+        fn, dim, ch, par = key.split("_")
+        a = G["a1"] if dim == "1d" else G["a2"]
+        if fn == "derm":
+            r = ra.derm(a, ch, par)
+        else:
+            r = ra.dermv(a, G["b1"] if dim == "1d" else (G["b2l"] if ch == "l" else G["b2r"]), ch, par)
+        assert r.shape == G[key].shape and np.array_equal(r, G[key]), key
+        n += 1
+    assert n == 14
+    with pytest.raises(NotImplementedError):
+        ra.dermv(G["a1"], G["b1"], "r")

@@ -126,3 +126,25 @@ def test_live_reference_small():
     got = bo.gamma_ball_full(dP, theta, fl.bmag[0][0], fl.gradpar_theta_pest[0][0], cv, gd, method="lambda_max")
     np.testing.assert_allclose(got[0], ref[0], rtol=1e-10)
     np.testing.assert_allclose(sign_normalise(got[1]), sign_normalise(ref[1]), rtol=0, atol=1e-8)
+
+
+def _derm_cases(G):
+    for key in G.files:
+        if not key.startswith("derm"):
+            continue
+        fn, dim, ch, par = key.split("_")
+        a = G["a1"] if dim == "1d" else G["a2"]
+        b = None if fn == "derm" else (G["b1"] if dim == "1d" else (G["b2l"] if ch == "l" else G["b2r"]))
+        yield key, fn, a, b, ch, par
+
+
+def test_derm_dermv_restatement_matches_reference_golden(golden):
+    """f4 (part): the curvature penalty's finite-difference helpers, against vectors produced by the unmodified reference
+    (tests/golden/make_golden_derm.py) -- bit-exact, shapes included."""
+    G = golden("derm")
+    n = 0
+    for key, fn, a, b, ch, par in _derm_cases(G):
+        r = bo.derm(a, ch, par) if fn == "derm" else bo.dermv(a, b, ch, par)
+        assert r.shape == G[key].shape and np.array_equal(r, G[key]), key
+        n += 1
+    assert n == 14
