@@ -11,7 +11,7 @@
 // factorisation); inside the iteration they are used in a DIVISION-FREE form (state scaled by the running product of
 // the gh): 13 DFMA per row including the coefficient polynomials and the sum F z^2 of the Rayleigh-quotient step.
 // Without a chain of predecessors to warm-start from, the start value comes from the same pencil on coarser grids
-// (every 8th, 4th, 2nd point; Richardson-extrapolated), which costs ~4 fine-grid evaluations instead of ~12.
+// (every 16th, 8th, 4th, 2nd point; Richardson-extrapolated): ~5 fine-grid-equivalent evaluations instead of ~12.
 //
 // This header holds everything a lane computes, templated on a context that supplies the coefficient records and the
 // warp votes: the CUDA context (ibs_scan_solver.cu) streams the records through shared memory with TMA bulk copies;

@@ -3,13 +3,14 @@
 // Replaces the theta0 loop around gamma_ball_full (/root/reference/ball_scan.py:262-274, utils.py:1550-1624) for
 // batches in which every field line is solved for a row of theta0 values.
 //   scan_prep_kernel   one CTA per field line: the six theta0-independent coefficient rows of the line as 48-byte
-//                      records, for the fine grid and up to three coarser ones (every 2nd/4th/8th point), scaled by a
-//                      power of two so that max g ~ 1; bounds of the spectrum valid for the line's whole theta0 range
+//                      records, for the fine grid and up to four coarser ones (every 2nd/4th/8th/16th point), scaled by
+//                      a power of two so that max g ~ 1; bounds of the spectrum valid for the line's whole theta0 range
 //   scan_solve_kernel  persistent warps; a warp takes (line, group of 32*SPL theta0) items from a global counter.
 //                      The records are streamed through a per-warp ring of shared-memory tiles with TMA bulk copies
-//                      (cp.async.bulk + mbarrier, 3 stages ahead); every lane reads the SAME record (broadcast LDS.128)
-//                      and advances its own solve(s).  No shuffles, no block barriers, no per-solve set-up; HBM
-//                      traffic is the records once (they stay in L2 for the ~10 passes of an item) plus the outputs.
+//                      (cp.async.bulk + mbarrier, a ring of 3 stages: two ahead); every lane reads the SAME record
+//                      (broadcast LDS.128) and advances its own solve.  No shuffles in the passes, no block barriers, no
+//                      per-solve set-up; the state no loop touches lives in shared memory (one block per thread); HBM
+//                      traffic is the records once (they stay in L2 for the ~23 passes of an item) plus the outputs.
 #include <cstdlib>
 
 #include "ibs_common.cuh"
