@@ -181,8 +181,6 @@ def run_reference_arm(args):
         return
     kind, s, alpha, theta0, theta = workload_grids(args.workload)
     vals = []
-    for _ in range(max(1, args.warmup > 0) + 0):
-        pass
     t_all = time.perf_counter()
     steps = max(1, min(args.steps, 3))
     for _ in range(steps):

@@ -17,8 +17,6 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libibs_b200.so")
 SOURCES = ["ibs_api.cu", "ibs_solver.cu", "ibs_scan_solver.cu", "ibs_geometry.cu", "ibs_adjoint.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--use_fast_math=false".replace("=false", "") and "-DIBS_BUILD"]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-DIBS_BUILD", "-fmad=true"]
 
 
@@ -31,7 +29,8 @@ def _nvcc():
 
 def _stamp():
     h = hashlib.sha256()
-    for name in sorted(os.listdir(CSRC)) + ["../../include/ibs_b200.h"]:
+    names = [n for n in sorted(os.listdir(CSRC)) if n.endswith((".cu", ".cuh", ".h"))]
+    for name in names + ["../../include/ibs_b200.h"]:
         with open(os.path.join(CSRC, name), "rb") as f:
             h.update(name.encode() + f.read())
     h.update(" ".join(NVCC_FLAGS).encode())

@@ -1,6 +1,7 @@
 // C ABI of the library (see include/ibs_b200.h).  Thin argument checking + dispatch; no torch types.
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -47,6 +48,12 @@ int num_sms() {
     return cached[dev];
 }
 
+int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < IBS_MAX_DEVICES ? dev : IBS_MAX_DEVICES - 1;
+}
+
 // Warm-start chain used by the scan entry points: consecutive theta0 of one field line (the reference chains
 // its ARPACK start vector through the same loop, ball_scan.py:265-274).  The run length divides nth0.
 static int scan_chain_len(int nth0) {
@@ -78,6 +85,29 @@ __global__ void count_bad_kernel(const int* __restrict__ info, long long n, int*
     const bool bad = i < n && ((info[i] >> 16) & (IBS_FLAG_NOT_CONVERGED | IBS_FLAG_BAD_INPUT));
     const unsigned m = __ballot_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
+}
+
+// Streams and events of ibs_scan_host, created once per device and reused by every call.
+constexpr int MAX_HOST_CHUNKS = 8;
+struct HostCtx {
+    std::mutex mu;
+    cudaStream_t st_h = nullptr, st = nullptr, st_d = nullptr;
+    std::vector<cudaEvent_t> ev_h, ev_c;
+    cudaEvent_t ev_alloc = nullptr, ev_done = nullptr;
+    int ensure(int nchunk) {
+        if (!st_h) IBS_CUDA_CHECK(cudaStreamCreateWithFlags(&st_h, cudaStreamNonBlocking));
+        if (!st) IBS_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        if (!st_d) IBS_CUDA_CHECK(cudaStreamCreateWithFlags(&st_d, cudaStreamNonBlocking));
+        if (!ev_alloc) IBS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+        if (!ev_done) IBS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+        while ((int)ev_h.size() < nchunk) { cudaEvent_t e; IBS_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ev_h.push_back(e); }
+        while ((int)ev_c.size() < nchunk) { cudaEvent_t e; IBS_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ev_c.push_back(e); }
+        return IBS_OK;
+    }
+};
+static HostCtx& host_ctx() {
+    static HostCtx ctx[IBS_MAX_DEVICES];
+    return ctx[current_device_slot()];
 }
 
 static SolveParams blank_params() { SolveParams p; std::memset(&p, 0, sizeof(p)); return p; }
@@ -181,15 +211,20 @@ int ibs_obj_w_grad_batch(const double* base3, const double* dPdrho3, const doubl
     IBS_REQUIRE(npoint >= 0 && N >= 5 && h > 0.0 && del_alpha != 0.0, "bad sizes");
     if (npoint == 0) return IBS_OK;
     IBS_REQUIRE(base3 && dPdrho3 && theta0 && val_out && grad_out, "null pointer");
+    IBS_REQUIRE((long long)npoint * 3 <= 0x7fffffffLL, "npoint too large (3 * npoint field lines must fit an int)");
     cudaStream_t st = (cudaStream_t)stream;
-    // stream-ordered scratch: centre-line indices, lambda, and X / dX when the caller does not want them
-    int* line = nullptr; double* lam = nullptr; double* Xw = nullptr; double* dXw = nullptr;
-    IBS_CUDA_CHECK(cudaMallocAsync((void**)&line, (size_t)npoint * sizeof(int), st));
-    IBS_CUDA_CHECK(cudaMallocAsync((void**)&lam, (size_t)npoint * sizeof(double), st));
-    if (!X_out) IBS_CUDA_CHECK(cudaMallocAsync((void**)&Xw, (size_t)npoint * N * sizeof(double), st));
-    if (!dX_out) IBS_CUDA_CHECK(cudaMallocAsync((void**)&dXw, (size_t)npoint * N * sizeof(double), st));
-    double* X = X_out ? X_out : Xw;
-    double* dX = dX_out ? dX_out : dXw;
+    // stream-ordered scratch: centre-line indices, lambda, and X / dX when the caller does not want them -- ONE
+    // allocation, so that no error path can leak a part of it
+    const size_t o_line = 0, o_lam = ((size_t)npoint * sizeof(int) + 255) & ~(size_t)255;
+    const size_t o_X = o_lam + (((size_t)npoint * sizeof(double) + 255) & ~(size_t)255);
+    const size_t xbytes = ((size_t)npoint * N * sizeof(double) + 255) & ~(size_t)255;
+    const size_t o_dX = o_X + (X_out ? 0 : xbytes), total = o_dX + (dX_out ? 0 : xbytes);
+    char* ws = nullptr;
+    IBS_CUDA_CHECK(cudaMallocAsync((void**)&ws, total + 256, st));
+    int* line = (int*)(ws + o_line);
+    double* lam = (double*)(ws + o_lam);
+    double* X = X_out ? X_out : (double*)(ws + o_X);
+    double* dX = dX_out ? dX_out : (double*)(ws + o_dX);
     int rc = launch_centre_lines(line, npoint, st);
     if (rc == IBS_OK) {
         SolveParams p = blank_params();
@@ -199,9 +234,7 @@ int ibs_obj_w_grad_batch(const double* base3, const double* dPdrho3, const doubl
         rc = solve_dispatch(p, true, false, st);
     }
     if (rc == IBS_OK) rc = launch_obj_grad(base3, dPdrho3, theta0, lam, X, dX, npoint, N, del_alpha, val_out, grad_out, st);
-    cudaFreeAsync(line, st); cudaFreeAsync(lam, st);
-    if (Xw) cudaFreeAsync(Xw, st);
-    if (dXw) cudaFreeAsync(dXw, st);
+    cudaFreeAsync(ws, st);
     return rc;
 }
 
@@ -220,15 +253,17 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
                   double* gamma_out, double* val_out, int* idx_out, double* sigma0_out, double* xbest_out, int* nbad_out) {
     IBS_REQUIRE(tab_mn && tab_nyq && scal && alpha && theta0 && theta && gamma_out, "null pointer");
     IBS_REQUIRE(ns >= 1 && nalpha >= 1 && nth0 >= 1 && nl >= 3, "bad sizes");
+    IBS_REQUIRE((long long)ns * nalpha * nth0 <= 0x7fffffffLL, "ns * nalpha * nth0 must fit an int");
     keep_pool_cached();
     // Three streams: uploads, compute, downloads.  The surfaces are processed in chunks (every chunk: tables up ->
     // K1 -> K2+K3 -> arg-max -> eigenfunction of each surface's maximum -> results down), so that the copies of one chunk
     // overlap the kernels of its neighbours; a chunk keeps >= 4 rounds of the solver's resident warps busy (measured on
     // the D3D config x 37 equilibria: 1 / 2 / 4 chunks = 3.37e7 / 3.55e7 / 3.22e7 solves/s; IBS_HOST_CHUNKS overrides).
-    cudaStream_t st_h = nullptr, st = nullptr, st_d = nullptr;
-    IBS_CUDA_CHECK(cudaStreamCreateWithFlags(&st_h, cudaStreamNonBlocking));
-    IBS_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    IBS_CUDA_CHECK(cudaStreamCreateWithFlags(&st_d, cudaStreamNonBlocking));
+    // Streams and events are created once per device and reused (the call holds the device's context lock).
+    HostCtx& hc = host_ctx();
+    std::lock_guard<std::mutex> hold(hc.mu);
+    if (int rc0 = hc.ensure(MAX_HOST_CHUNKS)) return rc0;
+    cudaStream_t st_h = hc.st_h, st = hc.st, st_d = hc.st_d;
     const size_t nlines = (size_t)ns * nalpha, nsolve = nlines * nth0;
     const int ngrid = nalpha * nth0;
     int nchunk = 1;
@@ -236,7 +271,7 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
         const long long items = (long long)nlines * ((nth0 + 31) / 32), per_round = 8LL * num_sms();
         nchunk = (int)(items / (4 * per_round));
         if (const char* e = std::getenv("IBS_HOST_CHUNKS")) nchunk = std::atoi(e);
-        if (nchunk > 8) nchunk = 8;
+        if (nchunk > MAX_HOST_CHUNKS) nchunk = MAX_HOST_CHUNKS;
         if (nchunk > ns) nchunk = ns;
         if (nchunk < 1) nchunk = 1;
     }
@@ -253,15 +288,9 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
     char* d = nullptr;
     int rc = IBS_OK;
     int nbad_host = 0;
-    std::vector<cudaEvent_t> ev_h(nchunk, nullptr), ev_c(nchunk, nullptr);
-    cudaEvent_t ev_alloc = nullptr, ev_done = nullptr;
+    std::vector<cudaEvent_t>& ev_h = hc.ev_h; std::vector<cudaEvent_t>& ev_c = hc.ev_c;
+    cudaEvent_t ev_alloc = hc.ev_alloc, ev_done = hc.ev_done;
 #define IBS_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { rc = cuda_fail(_e, #expr); goto done; } } while (0)
-    for (int c = 0; c < nchunk; ++c) {
-        IBS_TRY(cudaEventCreateWithFlags(&ev_h[c], cudaEventDisableTiming));
-        IBS_TRY(cudaEventCreateWithFlags(&ev_c[c], cudaEventDisableTiming));
-    }
-    IBS_TRY(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
-    IBS_TRY(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
     IBS_TRY(cudaMallocAsync((void**)&d, off, st));
     IBS_TRY(cudaEventRecord(ev_alloc, st));
     IBS_TRY(cudaStreamWaitEvent(st_h, ev_alloc, 0));
@@ -335,11 +364,6 @@ done:
     if (rc != IBS_OK) { cudaStreamSynchronize(st_h); cudaStreamSynchronize(st); cudaStreamSynchronize(st_d); }
     if (d) cudaFreeAsync(d, st);
     cudaStreamSynchronize(st);
-    for (auto e : ev_h) if (e) cudaEventDestroy(e);
-    for (auto e : ev_c) if (e) cudaEventDestroy(e);
-    if (ev_alloc) cudaEventDestroy(ev_alloc);
-    if (ev_done) cudaEventDestroy(ev_done);
-    cudaStreamDestroy(st_h); cudaStreamDestroy(st); cudaStreamDestroy(st_d);
     return rc;
 }
 

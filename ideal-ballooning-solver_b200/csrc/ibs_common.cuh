@@ -27,6 +27,10 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 int num_sms();
+// Index of the current device, clamped to [0, IBS_MAX_DEVICES): per-device "configured once" flags and caches are
+// keyed by it (function attributes such as the dynamic shared-memory limit are per device, not per process).
+constexpr int IBS_MAX_DEVICES = 64;
+int current_device_slot();
 // Keep stream-ordered allocations cached in the device's default memory pool between calls (by default the pool
 // hands everything back to the driver at the next synchronisation, so every call would pay cudaMalloc again).
 void keep_pool_cached();

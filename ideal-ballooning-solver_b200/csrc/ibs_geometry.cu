@@ -477,10 +477,11 @@ static int launch_geometry(const GeoParams& p, cudaStream_t st) {
     const size_t e_mn = (NT1 > 0) ? (size_t)(NT1 + 1) * ROWP_MN : (size_t)ROW_MN, e_nyq = (NT2 > 0) ? (size_t)(NT2 + 1) * ROWP_NYQ : (size_t)ROW_NYQ;
     const size_t smem = 16 + ((size_t)p.M1 * e_mn + (size_t)p.M2 * e_nyq) * sizeof(double);
     if (smem > 200 * 1024) { set_error("Fourier tables of one surface do not fit in shared memory"); return IBS_ERR_UNSUPPORTED; }
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[IBS_MAX_DEVICES] = {false};     // per instantiation and per device (the attribute is per device)
+    const int dslot = current_device_slot();
+    if (!configured[dslot]) {
         IBS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
+        configured[dslot] = true;
     }
     int per_sm = 0;
     IBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GEO_THREADS, smem));
@@ -537,18 +538,20 @@ int geometry_dispatch(const double* tab_mn, const double* tab_nyq, const double*
     {
         // The mode layout of an equilibrium family never changes between calls: keep the last one on
         // the device so steady-state calls issue no host->device copy and no host synchronisation.
+        // One slot per device (a process may drive several GPUs); a replaced layout is freed after a device-wide
+        // synchronisation, because launches on other streams may still read it.
+        struct ModeCache { std::vector<int> host; int* dev = nullptr; };
         static std::mutex mu;
-        static std::vector<int> cached; static int* cached_dev = nullptr; static int cached_device = -1;
+        static ModeCache cache[IBS_MAX_DEVICES];
         std::lock_guard<std::mutex> lk(mu);
-        int dev = 0; IBS_CUDA_CHECK(cudaGetDevice(&dev));
-        if (!(cached_dev && cached_device == dev && cached == h_idx)) {
-            if (cached_dev && cached_device == dev) { IBS_CUDA_CHECK(cudaStreamSynchronize(st)); cudaFree(cached_dev); }
-            cached_dev = nullptr;
-            IBS_CUDA_CHECK(cudaMalloc((void**)&cached_dev, h_idx.size() * sizeof(int)));
-            IBS_CUDA_CHECK(cudaMemcpy(cached_dev, h_idx.data(), h_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
-            cached = h_idx; cached_device = dev;
+        ModeCache& mc = cache[current_device_slot()];
+        if (!(mc.dev && mc.host == h_idx)) {
+            if (mc.dev) { IBS_CUDA_CHECK(cudaDeviceSynchronize()); cudaFree(mc.dev); mc.dev = nullptr; mc.host.clear(); }
+            IBS_CUDA_CHECK(cudaMalloc((void**)&mc.dev, h_idx.size() * sizeof(int)));
+            IBS_CUDA_CHECK(cudaMemcpy(mc.dev, h_idx.data(), h_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+            mc.host = h_idx;
         }
-        d_idx = cached_dev;
+        d_idx = mc.dev;
     }
     keep_pool_cached();
     IBS_CUDA_CHECK(cudaMallocAsync((void**)&pk, (n_mn + n_nyq) * sizeof(double), st));

@@ -296,11 +296,12 @@ static int scan_launch(const ScanParams& sp, cudaStream_t stream) {
     auto kern = scan_solve_kernel<SPL, MODE>;
     const size_t smem = (size_t)SC_WARPS * SC_RING * sizeof(double) + (size_t)SC_WARPS * SC_NSTAGE * sizeof(uint64_t) +
                         (size_t)SC_WARPS * 32 * ColdStride<SPL>::value * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[IBS_MAX_DEVICES] = {false};     // per instantiation and per device (the attribute is per device)
+    const int dslot = current_device_slot();
+    if (!configured[dslot]) {
         IBS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IBS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        configured = true;
+        configured[dslot] = true;
     }
     int per_sm = 0;
     IBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SC_WARPS * 32, smem));

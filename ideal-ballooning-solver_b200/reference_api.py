@@ -100,21 +100,16 @@ def gamma_ball_full(dPdrho, theta_PEST, B, gradpar, cvdrift, gds2, vguess=None, 
     uniform = np.array_equal(tu, theta) or np.allclose(np.diff(theta), tu[1] - tu[0], rtol=1e-12, atol=0)
     for k, a in rows.items():
         a = np.asarray(a, dtype=np.float64)
-        base[0, k] = a if uniform else np.interp(tu, theta, a)
+        base[0, k] = a
     if not uniform:
-        # g, c, f are interpolated by the reference, not the base arrays; on a non-uniform grid fall back to its order
-        g = np.abs(gradpar) * gds2 / (B)
-        c = -1 * dPdrho * cvdrift * 1 / (np.abs(gradpar) * B)
-        f = gds2 / np.asarray(B) ** 2 * 1 / (np.abs(gradpar) * B)
-        g, c, f = (np.interp(tu, theta, a) for a in (g, c, f))
-        sol = engine.solve_gcf_batch(g[None], c[None], f[None], engine.grid_spacing(theta),
-                                     sigma=torch.tensor([float(sigma0)], dtype=torch.float64))
-        gcf = (g, c, f)
-    else:
-        sol = engine.solve_base_batch(torch.from_numpy(base).cuda(), torch.tensor([float(dPdrho)], dtype=torch.float64),
-                                      torch.zeros(1, dtype=torch.float64), engine.grid_spacing(theta), nth0=1,
-                                      sigma=torch.tensor([float(sigma0)], dtype=torch.float64), want_gcf=True)
-        gcf = tuple(t[0].cpu().numpy() for t in (sol.g, sol.c, sol.f))
+        # On a non-uniform grid the reference interpolates g, c, f to a uniform grid but takes the half-point g from the
+        # ORIGINAL grid (utils.py:1567-1576), which the kernels' (g_j + g_j+1) / 2 does not reproduce.  Every caller in the
+        # reference passes np.linspace grids (ball_scan.py:203-208), so this is rejected rather than approximated.
+        raise NotImplementedError("gamma_ball_full: theta_PEST must be equispaced (as in every reference call site)")
+    sol = engine.solve_base_batch(torch.from_numpy(base).cuda(), torch.tensor([float(dPdrho)], dtype=torch.float64),
+                                  torch.zeros(1, dtype=torch.float64), engine.grid_spacing(theta), nth0=1,
+                                  sigma=torch.tensor([float(sigma0)], dtype=torch.float64), want_gcf=True)
+    gcf = tuple(t[0].cpu().numpy() for t in (sol.g, sol.c, sol.f))
     flags = int(sol.flags[0].item())
     if flags & engine.FLAG_BAD_INPUT:
         raise ValueError("gamma_ball_full: non-finite input or g <= 0 / f <= 0 on the field line")

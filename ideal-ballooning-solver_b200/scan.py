@@ -122,9 +122,16 @@ def sharded_coarse_scan(st: SurfaceTables, alpha, theta0, theta, device=None, wa
         rank, world = 0, 1
     lo, hi = shard_range(st.ns, rank, world)
     device = device or torch.device("cuda", torch.cuda.current_device())
-    dt = engine.DeviceTables.from_host(st.select(np.arange(lo, hi)), device)
-    res = coarse_scan(dt, alpha, theta0, theta, want_X=want_X)
-    val_all, idx_all = gather_surface_maxima(res.val, res.idx, st.ns, group)
+    if hi > lo:
+        dt = engine.DeviceTables.from_host(st.select(np.arange(lo, hi)), device)
+        res = coarse_scan(dt, alpha, theta0, theta, want_X=want_X)
+        val, idx = res.val, res.idx
+    else:
+        # more ranks than surfaces: this rank has nothing to scan but still takes part in the exchange
+        res = None
+        val = torch.empty((0,), dtype=torch.float64, device=device)
+        idx = torch.empty((0,), dtype=torch.int32, device=device)
+    val_all, idx_all = gather_surface_maxima(val, idx, st.ns, group)
     return res, (lo, hi), val_all, idx_all
 
 
@@ -172,16 +179,29 @@ class _BatchedObjective:
         self.nbatches += 1
         self.nevals += len(ids)
 
+    def _run_batch_guarded(self):
+        """Run the pending round; a failure (CUDA error, bad input, ...) becomes the result of EVERY pending surface, so
+        that no waiting thread is left behind (each of them re-raises it)."""
+        try:
+            self._run_batch()
+        except BaseException as e:          # noqa: BLE001 - handed to the waiting threads
+            for i in list(self.pending):
+                self.results[i] = e
+            self.pending.clear()
+        self.cv.notify_all()
+
     def evaluate(self, i, x):
         with self.cv:
             self.pending[i] = (float(x[0]), float(x[1]))
             if len(self.pending) == len(self.active):
-                self._run_batch()
-                self.cv.notify_all()
+                self._run_batch_guarded()
             else:
                 while i not in self.results:
                     self.cv.wait()
-            val, grad, flags = self.results.pop(i)
+            res = self.results.pop(i)
+        if isinstance(res, BaseException):
+            raise RuntimeError("obj_w_grad: batched evaluation failed (surface %d)" % i) from res
+        val, grad, flags = res
         if flags & (engine.FLAG_NOT_CONVERGED | engine.FLAG_BAD_INPUT):
             raise RuntimeError("obj_w_grad: eigen-solve failed on surface %d" % i)
         return val, grad
@@ -189,9 +209,9 @@ class _BatchedObjective:
     def finish(self, i):
         with self.cv:
             self.active.discard(i)
+            self.pending.pop(i, None)
             if self.pending and len(self.pending) == len(self.active):
-                self._run_batch()
-                self.cv.notify_all()
+                self._run_batch_guarded()
 
 
 @dataclasses.dataclass

@@ -9,8 +9,11 @@
  * Conventions
  *   - all arrays are fp64, row-major, caller-allocated; pointers are DEVICE pointers unless the
  *     function name ends in `_host`;
- *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), does not synchronise
- *     the host and keeps no global mutable state except the thread-local error string;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and does not synchronise
+ *     the host.  State kept between calls: the thread-local error string and, PER DEVICE and behind a
+ *     mutex, caches that never change results (kernel attributes set once, the device copy of the
+ *     last Fourier-mode layout, the streams/events of ibs_scan_host, the memory-pool threshold); one
+ *     process may therefore drive several GPUs (cudaSetDevice before the call);
  *   - return value 0 = OK, non-zero = error (see ibs_last_error());
  *   - there is no CPU fallback: without a CUDA device every compute call fails.
  *
