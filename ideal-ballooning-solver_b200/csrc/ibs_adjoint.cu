@@ -148,7 +148,7 @@ __global__ void centre_lines_kernel(int* line, int n) {
 // Per-surface arg-max with the guards of ball_scan.py:279-295.
 __global__ void __launch_bounds__(RED_THREADS)
 argmax_kernel(const double* __restrict__ gamma, int ngrid, double* __restrict__ val, int* __restrict__ idx,
-              double* __restrict__ sigma0) {
+              double* __restrict__ sigma0, double* __restrict__ best) {
     __shared__ double sv[RED_THREADS / 32];
     __shared__ int si[RED_THREADS / 32];
     __shared__ int snan[RED_THREADS / 32];
@@ -176,19 +176,14 @@ argmax_kernel(const double* __restrict__ gamma, int ngrid, double* __restrict__ 
             anynan |= snan[w];
             if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
         }
-        if (anynan) {                       // np.max propagates NaN; the reference would raise
-            val[s] = __longlong_as_double(0x7ff8000000000000LL);
-            idx[s] = -2;
-            if (sigma0) sigma0[s] = 0.05;
-        } else if (bv == 0.0) {             // ball_scan.py:279-282
-            val[s] = bv;
-            idx[s] = -1;
-            if (sigma0) sigma0[s] = 0.05;
-        } else {                            // ball_scan.py:283-295 (first index in row-major order)
-            val[s] = bv;
-            idx[s] = bi;
-            if (sigma0) sigma0[s] = 1.3 * fabs(bv) + 0.05;
-        }
+        double v; int k; double sg;
+        if (anynan) { v = __longlong_as_double(0x7ff8000000000000LL); k = -2; sg = 0.05; }     // np.max propagates NaN; the reference would raise
+        else if (bv == 0.0) { v = bv; k = -1; sg = 0.05; }                                      // ball_scan.py:279-282
+        else { v = bv; k = bi; sg = 1.3 * fabs(bv) + 0.05; }                                    // ball_scan.py:283-295 (first index in row-major order)
+        if (val) val[s] = v;
+        if (idx) idx[s] = k;
+        if (sigma0) sigma0[s] = sg;
+        if (best) { best[2 * s] = v; best[2 * s + 1] = (double)k; }     // packed (max, index) pair: the all-gather send slot
     }
 }
 
@@ -207,20 +202,25 @@ int launch_gather_best(const double* X, const int* idx, int ns, int ngrid, int N
     return IBS_OK;
 }
 
-// (line, theta0) of each surface's arg-max solve (flat index 0 when the all-zero guard fired)
-__global__ void best_setup_kernel(const int* __restrict__ idx, const double* __restrict__ theta0, int ns, int ngrid, int nth0,
-                                  int* __restrict__ line_out, double* __restrict__ th0_out) {
+// Unpack the (max, index) pairs of the fused arg-max: val / idx arrays for the host, and the (line, theta0) of each
+// surface's arg-max solve (flat index 0 when the all-zero guard fired) for the eigenfunction re-solve
+__global__ void best_setup_kernel(const double* __restrict__ best, const double* __restrict__ theta0, int ns, int ngrid, int nth0,
+                                  double* __restrict__ val_out, int* __restrict__ idx_out, int* __restrict__ line_out,
+                                  double* __restrict__ th0_out) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= ns) return;
-    const int k = idx[s] < 0 ? 0 : idx[s];
+    const int idx = (int)best[2 * s + 1];
+    val_out[s] = best[2 * s];
+    idx_out[s] = idx;
+    const int k = idx < 0 ? 0 : idx;
     const int flat = s * ngrid + k;
     line_out[s] = flat / nth0;
     th0_out[s] = theta0[flat];
 }
-int launch_best_setup(const int* idx, const double* theta0, int ns, int ngrid, int nth0, int* line_out, double* th0_out,
-                      cudaStream_t st) {
+int launch_best_setup(const double* best, const double* theta0, int ns, int ngrid, int nth0, double* val_out, int* idx_out,
+                      int* line_out, double* th0_out, cudaStream_t st) {
     if (ns == 0) return IBS_OK;
-    best_setup_kernel<<<(ns + 127) / 128, 128, 0, st>>>(idx, theta0, ns, ngrid, nth0, line_out, th0_out);
+    best_setup_kernel<<<(ns + 127) / 128, 128, 0, st>>>(best, theta0, ns, ngrid, nth0, val_out, idx_out, line_out, th0_out);
     IBS_CUDA_CHECK(cudaGetLastError());
     return IBS_OK;
 }
@@ -256,7 +256,13 @@ int launch_centre_lines(int* line, int n, cudaStream_t st) {
 }
 int launch_argmax(const double* gamma, int ns, int ngrid, double* val, int* idx, double* sigma0, cudaStream_t st) {
     if (ns == 0) return IBS_OK;
-    argmax_kernel<<<ns, RED_THREADS, 0, st>>>(gamma, ngrid, val, idx, sigma0);
+    argmax_kernel<<<ns, RED_THREADS, 0, st>>>(gamma, ngrid, val, idx, sigma0, nullptr);
+    IBS_CUDA_CHECK(cudaGetLastError());
+    return IBS_OK;
+}
+int launch_argmax_packed(const double* gamma, int ns, int ngrid, double* best, double* sigma0, cudaStream_t st) {
+    if (ns == 0) return IBS_OK;
+    argmax_kernel<<<ns, RED_THREADS, 0, st>>>(gamma, ngrid, nullptr, nullptr, sigma0, best);
     IBS_CUDA_CHECK(cudaGetLastError());
     return IBS_OK;
 }

@@ -26,9 +26,11 @@ int launch_obj_grad(const double* base3, const double* dPdrho3, const double* th
                     double* grad, cudaStream_t st);
 int launch_centre_lines(int* line, int n, cudaStream_t st);
 int launch_argmax(const double* gamma, int ns, int ngrid, double* val, int* idx, double* sigma0, cudaStream_t st);
+int launch_argmax_packed(const double* gamma, int ns, int ngrid, double* best, double* sigma0, cudaStream_t st);
+bool scan_solver_eligible(const SolveParams& p);
 int launch_gather_best(const double* X, const int* idx, int ns, int ngrid, int N, double* out, cudaStream_t st);
-int launch_best_setup(const int* idx, const double* theta0, int ns, int ngrid, int nth0, int* line_out, double* th0_out,
-                      cudaStream_t st);
+int launch_best_setup(const double* best, const double* theta0, int ns, int ngrid, int nth0, double* val_out, int* idx_out,
+                      int* line_out, double* th0_out, cudaStream_t st);
 
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
@@ -110,6 +112,24 @@ static HostCtx& host_ctx() {
     return ctx[current_device_slot()];
 }
 
+// FP64 peak probe: independent DFMA chains, 8 per thread, 32 warps per SM (the denominator of the FP64-pipe rooflines)
+constexpr int PROBE_CHAINS = 8, PROBE_UNROLL = 16, PROBE_THREADS = 256, PROBE_CTAS_PER_SM = 4;
+__global__ void __launch_bounds__(PROBE_THREADS) fp64_probe_kernel(double* __restrict__ out, int iters, double a, double b) {
+    double x[PROBE_CHAINS];
+#pragma unroll
+    for (int c = 0; c < PROBE_CHAINS; ++c) x[c] = 1e-3 * threadIdx.x + c;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < PROBE_UNROLL; ++u)
+#pragma unroll
+            for (int c = 0; c < PROBE_CHAINS; ++c) x[c] = fma(x[c], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < PROBE_CHAINS; ++c) s += x[c];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 static SolveParams blank_params() { SolveParams p; std::memset(&p, 0, sizeof(p)); return p; }
 
 }  // namespace ibs
@@ -129,6 +149,16 @@ int ibs_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     if (sm_count) *sm_count = prop.multiProcessorCount;
     if (cc_major) *cc_major = prop.major;
     if (cc_minor) *cc_minor = prop.minor;
+    return IBS_OK;
+}
+
+int ibs_fp64_probe(int iters, double* scratch, long long scratch_len, double* fma_count_out, void* stream) {
+    IBS_REQUIRE(iters >= 1 && scratch && fma_count_out, "bad arguments");
+    const int grid = num_sms() * PROBE_CTAS_PER_SM;
+    IBS_REQUIRE(scratch_len >= (long long)grid * PROBE_THREADS, "scratch too small (need 4 * SMs * 256 doubles)");
+    fp64_probe_kernel<<<grid, PROBE_THREADS, 0, (cudaStream_t)stream>>>(scratch, iters, 0.999, 1e-3);
+    IBS_CUDA_CHECK(cudaGetLastError());
+    *fma_count_out = (double)grid * PROBE_THREADS * (double)iters * PROBE_UNROLL * PROBE_CHAINS;
     return IBS_OK;
 }
 
@@ -176,6 +206,29 @@ int ibs_solve_base_batch(const double* base, const double* dPdrho, const double*
     p.lam_out = lam_out; p.lam_matrix_out = lam_matrix_out; p.X_out = X_out; p.dX_out = dX_out;
     p.g_out = g_out; p.c_out = c_out; p.f_out = f_out; p.info_out = info_out;
     return solve_dispatch(p, true, false, (cudaStream_t)stream);
+}
+
+int ibs_scan_solve_argmax(const double* base, const double* dPdrho, const double* theta0, int nth0, int nline,
+                          int lines_per_surface, int N, double h, const double* sigma, int chain_len,
+                          double* lam_out, double* X_out, double* dX_out, int* info_out,
+                          double* best_out, double* sigma0_out, void* stream) {
+    IBS_REQUIRE(nline >= 0 && nth0 >= 1 && N >= 5 && h > 0.0, "bad sizes");
+    IBS_REQUIRE(lines_per_surface >= 1 && nline % lines_per_surface == 0, "nline must be a multiple of lines_per_surface");
+    IBS_REQUIRE((long long)nline * nth0 <= 0x7fffffffLL, "nline * nth0 must fit an int");
+    if (nline == 0) return IBS_OK;
+    IBS_REQUIRE(base && dPdrho && theta0 && lam_out && best_out, "null pointer");
+    keep_pool_cached();
+    SolveParams p = blank_params();
+    p.base = base; p.dPdrho = dPdrho; p.theta0 = theta0; p.nth0 = nth0; p.nsolve = nline * nth0; p.N = N; p.h = h;
+    p.sigma = sigma; p.chain_len = chain_len;
+    p.lam_out = lam_out; p.X_out = X_out; p.dX_out = dX_out; p.info_out = info_out;
+    p.lines_per_surface = lines_per_surface; p.best_out = best_out; p.sigma0_out = sigma0_out;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool fused = scan_solver_eligible(p);            // the lane-per-solve kernel reduces in its epilogue
+    int rc = solve_dispatch(p, true, false, st);
+    if (rc == IBS_OK && !fused)
+        rc = launch_argmax_packed(lam_out, nline / lines_per_surface, lines_per_surface * nth0, best_out, sigma0_out, st);
+    return rc;
 }
 
 int ibs_count_above_batch(const double* g, const double* c, const double* f, int nsolve, int N, double h,
@@ -250,7 +303,8 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
                   int ns, int mnmax, int mnmax_nyq, double phiedge, double aminor_p,
                   const double* alpha, int nalpha, const double* theta0, int nth0,
                   const double* theta, int nl, double h,
-                  double* gamma_out, double* val_out, int* idx_out, double* sigma0_out, double* xbest_out, int* nbad_out) {
+                  double* gamma_out, double* val_out, int* idx_out, double* sigma0_out, double* xbest_out, double* xall_out,
+                  int* nbad_out) {
     IBS_REQUIRE(tab_mn && tab_nyq && scal && alpha && theta0 && theta && gamma_out, "null pointer");
     IBS_REQUIRE(ns >= 1 && nalpha >= 1 && nth0 >= 1 && nl >= 3, "bad sizes");
     IBS_REQUIRE((long long)ns * nalpha * nth0 <= 0x7fffffffLL, "ns * nalpha * nth0 must fit an int");
@@ -284,7 +338,8 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
                  o_dp = take(nlines * 8), o_gam = take(nsolve * 8), o_val = take((size_t)ns * 8), o_sig = take((size_t)ns * 8),
                  o_idx = take((size_t)ns * 4), o_info = take(nsolve * 4),
                  o_xb = take(xbest_out ? (size_t)ns * nl * 8 : 0), o_bl = take((size_t)ns * 4), o_bt = take((size_t)ns * 8),
-                 o_bg = take((size_t)ns * 8), o_t0h = take((size_t)nth0 * 8), o_nb = take(4);
+                 o_bg = take((size_t)ns * 8), o_t0h = take((size_t)nth0 * 8), o_nb = take(4), o_best = take((size_t)ns * 16),
+                 o_xa = take(xall_out ? nsolve * nl * 8 : 0);
     char* d = nullptr;
     int rc = IBS_OK;
     int nbad_host = 0;
@@ -321,27 +376,33 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
                                (double*)(d + o_th), nl, 0.0, base_c, dp_c, nullptr, nullptr, st);
         if (rc != IBS_OK) goto done;
         {
+            // K2+K3 with the per-surface arg-max fused into the solver's epilogue (one packed (max, index) pair per surface)
             SolveParams p = blank_params();
             p.base = base_c; p.dPdrho = dp_c; p.theta0 = (double*)(d + o_t0) + v0; p.nth0 = nth0;
             p.nsolve = (int)nvc; p.N = nl; p.h = h; p.lam_out = (double*)(d + o_gam) + v0; p.info_out = (int*)(d + o_info) + v0;
+            p.X_out = xall_out ? (double*)(d + o_xa) + v0 * nl : nullptr;
             p.chain_len = scan_chain_len(nth0);
+            p.lines_per_surface = nalpha; p.best_out = (double*)(d + o_best) + 2 * s0; p.sigma0_out = (double*)(d + o_sig) + s0;
+            const bool fused = scan_solver_eligible(p);
             rc = solve_dispatch(p, true, false, st);
+            if (rc == IBS_OK && !fused) rc = launch_argmax_packed(p.lam_out, (int)nsc, ngrid, p.best_out, p.sigma0_out, st);
             if (rc != IBS_OK) goto done;
         }
-        rc = launch_argmax((double*)(d + o_gam) + v0, (int)nsc, ngrid, (double*)(d + o_val) + s0, (int*)(d + o_idx) + s0,
-                           (double*)(d + o_sig) + s0, st);
+        // val / idx for the host and the (line, theta0) of each surface's maximum; line indices are chunk-local
+        rc = launch_best_setup((double*)(d + o_best) + 2 * s0, (double*)(d + o_t0) + v0, (int)nsc, ngrid, nth0, (double*)(d + o_val) + s0,
+                               (int*)(d + o_idx) + s0, (int*)(d + o_bl) + s0, (double*)(d + o_bt) + s0, st);
         if (rc != IBS_OK) goto done;
-        if (xbest_out) {
+        if (xbest_out && !xall_out) {
             // eigenfunction of each surface's arg-max only: re-solve those problems with the eigenvector written out
-            // (instead of writing nsolve eigenvectors and gathering ns of them); line indices are chunk-local
-            rc = launch_best_setup((int*)(d + o_idx) + s0, (double*)(d + o_t0) + v0, (int)nsc, ngrid, nth0, (int*)(d + o_bl) + s0,
-                                   (double*)(d + o_bt) + s0, st);
-            if (rc != IBS_OK) goto done;
+            // (instead of writing nsolve eigenvectors and gathering ns of them)
             SolveParams pb = blank_params();
             pb.base = base_c; pb.dPdrho = dp_c; pb.theta0 = (double*)(d + o_bt) + s0;
             pb.line_of_solve = (int*)(d + o_bl) + s0; pb.nth0 = 1; pb.nsolve = (int)nsc; pb.N = nl; pb.h = h;
             pb.lam_out = (double*)(d + o_bg) + s0; pb.X_out = (double*)(d + o_xb) + s0 * nl;
             rc = solve_dispatch(pb, true, false, st);
+            if (rc != IBS_OK) goto done;
+        } else if (xbest_out) {
+            rc = launch_gather_best((double*)(d + o_xa) + v0 * nl, (int*)(d + o_idx) + s0, (int)nsc, ngrid, nl, (double*)(d + o_xb) + s0 * nl, st);
             if (rc != IBS_OK) goto done;
         }
         count_bad_kernel<<<(unsigned)((nvc + 255) / 256), 256, 0, st>>>((int*)(d + o_info) + v0, (long long)nvc, (int*)(d + o_nb));
@@ -353,6 +414,7 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
         if (idx_out) IBS_TRY(cudaMemcpyAsync(idx_out + s0, d + o_idx + s0 * 4, nsc * 4, cudaMemcpyDeviceToHost, st_d));
         if (sigma0_out) IBS_TRY(cudaMemcpyAsync(sigma0_out + s0, d + o_sig + s0 * 8, nsc * 8, cudaMemcpyDeviceToHost, st_d));
         if (xbest_out) IBS_TRY(cudaMemcpyAsync(xbest_out + s0 * nl, d + o_xb + s0 * nl * 8, nsc * nl * 8, cudaMemcpyDeviceToHost, st_d));
+        if (xall_out) IBS_TRY(cudaMemcpyAsync(xall_out + v0 * nl, d + o_xa + v0 * nl * 8, nvc * nl * 8, cudaMemcpyDeviceToHost, st_d));
     }
     IBS_TRY(cudaMemcpyAsync(&nbad_host, d + o_nb, 4, cudaMemcpyDeviceToHost, st_d));
     IBS_TRY(cudaEventRecord(ev_done, st_d));

@@ -48,6 +48,10 @@ struct SolveParams {
     double* g_out; double* c_out; double* f_out; int* info_out;
     // count-only mode
     const double* lam_query; int* count_out;
+    // fused per-surface arg-max of a scan-shaped batch (ball_scan.py:279-295): lines_per_surface consecutive field lines form
+    // a surface; best_out [nsurf][2] = (max, first flat (line-in-surface, theta0) index as a double; -1: all-zero guard,
+    // -2: NaN), sigma0_out [nsurf] or null.  lines_per_surface = 0: off.
+    int lines_per_surface; double* best_out; double* sigma0_out;
 };
 
 constexpr unsigned FULL = 0xffffffffu;

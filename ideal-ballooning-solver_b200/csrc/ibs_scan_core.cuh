@@ -273,11 +273,15 @@ IBS_PASS void eval_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SP
     int i_first = 2;
     if (nfs > 0) {
         // ---- fast region: steps 2 .. 32 nfs - 1, ONE software pipeline across the stage boundaries (records two steps
-        // ahead through running pointers, coefficients one step ahead); waits / releases happen inside the loop
+        // ahead through running pointers, coefficients one step ahead).  Control flow is kept out of the hot code: the
+        // only branches are the back edges of counted loops over blocks of four steps (a taken branch costs a warp
+        // ~15 idle cycles, and with two warps per scheduler nothing hides them).  A trip of the stage loop covers the
+        // steps 32 m - 2 .. 32 m + 29, whose records all lie in stage m: wait / pointer reset at its top, rescaling
+        // after each half, release of the previous stage in the middle (its last records were consumed by the first
+        // block), sign histories of exactly 32 steps counted at the end.
         const int gend = TR * nfs;
         Co cf[SPL], cb[SPL];
         unsigned mf[SPL], mb[SPL], ef[SPL], eb[SPL];
-        int hn = 0;                                       // steps in the sign histories
         const double* pf = ctx.frec(2);
         const double* pb = ctx.brec(2);
         {
@@ -286,52 +290,54 @@ IBS_PASS void eval_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SP
             for (int q = 0; q < SPL; ++q) {
                 coef_next(f, th0[q], lam[q], gf[q], cf[q]);
                 coef_next(b, th0[q], lam[q], gb[q], cb[q]);
-                mf[q] = 0; mb[q] = 0; ef[q] = sign_bit(Xf[q]); eb[q] = sign_bit(Xb[q]);
+                // the first trip records 28 steps only: the history is pre-filled with the entering sign
+                ef[q] = sign_bit(Xf[q]); eb[q] = sign_bit(Xb[q]);
+                mf[q] = 0u - ef[q]; mb[q] = 0u - eb[q];
             }
         }
         pf += REC; pb -= REC;
         Rec rf = load_rec(pf), rb = load_rec(pb);         // records of step 3
-        pf += REC; pb -= REC;
-        auto flush = [&](int g_done) {                    // after step g_done (g_done % 16 == 15)
+        pf += REC; pb -= REC;                              // -> records of step 4
+        auto step1 = [&](const Rec& af, const Rec& ab) {   // chains of one step + coefficients of the next one from (af, ab)
 #pragma unroll
-            for (int q = 0; q < SPL; ++q) { rescale3(Xf[q], Wf[q], Sf[q]); rescale3(Xb[q], Wb[q], Sb[q]); }
-            if ((g_done & (TR - 1)) == TR - 1) {
-#pragma unroll
-                for (int q = 0; q < SPL; ++q) {
-                    nodes[q] += sign_changes_n(mf[q], hn, ef[q]) + sign_changes_n(mb[q], hn, eb[q]);
-                    mf[q] = 0; mb[q] = 0; ef[q] = sign_bit(Xf[q]); eb[q] = sign_bit(Xb[q]);
-                }
-                hn = 0;
-                ctx.release(g_done / TR);                 // every record of that stage has been consumed
+            for (int q = 0; q < SPL; ++q) {
+                joint_step(af, ab, th0[q], lam[q], cf[q], cb[q], gf[q], gb[q], Xf[q], Wf[q], Sf[q], Xb[q], Wb[q], Sb[q], tb[q]);
+                mf[q] = (mf[q] << 1) | sign_bit(Xf[q]);
+                mb[q] = (mb[q] << 1) | sign_bit(Xb[q]);
             }
         };
-        int g = 2;
+        auto blocks4 = [&](int nblk) {                     // nblk blocks of four steps; loads the records of the steps g+2 .. g+5
 #pragma unroll 1
-        for (; g + 3 < gend; g += 2) {
-            // step g (even): the records of step g + 2 may be the first ones of the next stage
-            if (((g + 2) & (TR - 1)) == 0) {
-                ctx.wait((g + 2) / TR);
-                pf = ctx.frec(0); pb = ctx.brec(0);
+            for (int b = 0; b < nblk; ++b) {
+                Rec nf = load_rec(pf), nb = load_rec(pb);
+                step1(rf, rb);
+                rf = load_rec(pf + REC); rb = load_rec(pb - REC);
+                step1(nf, nb);
+                nf = load_rec(pf + 2 * REC); nb = load_rec(pb - 2 * REC);
+                step1(rf, rb);
+                rf = load_rec(pf + 3 * REC); rb = load_rec(pb - 3 * REC);
+                step1(nf, nb);
+                pf += 4 * REC; pb -= 4 * REC;
             }
-            const Rec nf = load_rec(pf), nb = load_rec(pb);
-            pf += REC; pb -= REC;
+        };
+        auto rescale_all = [&]() {
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) { rescale3(Xf[q], Wf[q], Sf[q]); rescale3(Xb[q], Wb[q], Sb[q]); }
+        };
+#pragma unroll 1
+        for (int m = 0; m < nfs; ++m) {
+            if (m > 0) { ctx.wait(m); pf = ctx.frec(0); pb = ctx.brec(0); }
+            blocks4(m > 0 ? 4 : 3);                        // steps 32 m - 2 (m = 0: 2) .. 32 m + 13
+            rescale_all();
+            if (m > 0) ctx.release(m - 1);
+            blocks4(4);                                    // steps 32 m + 14 .. 32 m + 29
+            rescale_all();
 #pragma unroll
             for (int q = 0; q < SPL; ++q) {
-                joint_step(rf, rb, th0[q], lam[q], cf[q], cb[q], gf[q], gb[q], Xf[q], Wf[q], Sf[q], Xb[q], Wb[q], Sb[q], tb[q]);
-                mf[q] = (mf[q] << 1) | sign_bit(Xf[q]);
-                mb[q] = (mb[q] << 1) | sign_bit(Xb[q]);
+                nodes[q] += sign_changes32(mf[q], ef[q]) + sign_changes32(mb[q], eb[q]);
+                ef[q] = sign_bit(Xf[q]); eb[q] = sign_bit(Xb[q]);
+                mf[q] = 0; mb[q] = 0;
             }
-            // step g + 1 (odd)
-            rf = load_rec(pf); rb = load_rec(pb);
-            pf += REC; pb -= REC;
-#pragma unroll
-            for (int q = 0; q < SPL; ++q) {
-                joint_step(nf, nb, th0[q], lam[q], cf[q], cb[q], gf[q], gb[q], Xf[q], Wf[q], Sf[q], Xb[q], Wb[q], Sb[q], tb[q]);
-                mf[q] = (mf[q] << 1) | sign_bit(Xf[q]);
-                mb[q] = (mb[q] << 1) | sign_bit(Xb[q]);
-            }
-            hn += 2;
-            if (((g + 1) & 15) == 15) flush(g + 1);
         }
         // steps gend - 2 (its successor's coefficients from the record already loaded) and gend - 1 (chains only)
 #pragma unroll
@@ -343,9 +349,10 @@ IBS_PASS void eval_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SP
             bwd_chain(cb[q], Xb[q], Wb[q], Sb[q], tb[q]);
             mf[q] = (mf[q] << 1) | sign_bit(Xf[q]);
             mb[q] = (mb[q] << 1) | sign_bit(Xb[q]);
+            nodes[q] += sign_changes_n(mf[q], 2, ef[q]) + sign_changes_n(mb[q], 2, eb[q]);
         }
-        hn += 2;
-        flush(gend - 1);
+        rescale_all();
+        ctx.release(nfs - 1);
         s_next = nfs;
         i_first = 0;
     }
@@ -585,6 +592,7 @@ IBS_PASS void out_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL
     const int qf_end = k, qb_end = Nl - 1 - k;
     const int qmin = imin(qf_end, qb_end), qmax = imax(qf_end, qb_end);
     const int nst = qmax / TR + 1;
+    const int nfs = qmin / TR;                            // stages whose 32 steps are interior rows in both directions
     ctx.begin_pass(lev, Nl, k, nst);
     Sweep F_[SPL], B_[SPL];
     auto rescale_all = [&](bool do_f, bool do_b) {
@@ -594,104 +602,131 @@ IBS_PASS void out_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL
             if (do_b) sweep_rescale<WRITE>(B_[q]);
         }
     };
-    for (int s = 0; s < nst; ++s) {
-        ctx.wait(s);
-        int i0 = 0;
-        if (s == 0) {
-            const Rec f0 = load_rec(ctx.frec(0)), f1 = load_rec(ctx.frec(1));
-            const Rec b0 = load_rec(ctx.brec(0)), b1 = load_rec(ctx.brec(1));
+    // ---- stage 0: rows 0, 1 (and N-1, N-2) start the sweeps
+    ctx.wait(0);
+    {
+        const Rec f0 = load_rec(ctx.frec(0)), f1 = load_rec(ctx.frec(1));
+        const Rec b0 = load_rec(ctx.brec(0)), b1 = load_rec(ctx.brec(1));
 #pragma unroll
-            for (int q = 0; q < SPL; ++q) {
-                double g, C, Fv;
-                Sweep& f = F_[q]; Sweep& b = B_[q];
-                sweep_zero(f); sweep_zero(b);
-                if (WRITE) {
-                    const bool ok = !out[q].bad && out[q].zmax > 0.0 && out[q].zmax < 1e300;
-                    f.cn = ok ? NORM_INFLATE / (out[q].xkf * out[q].zmax) : 0.0;
-                    b.cn = ok ? NORM_INFLATE / (out[q].xkb * out[q].zmax) : 0.0;
-                    f.ex = -out[q].Ekf; b.ex = -out[q].Ekb;
-                    f.fsc = f.cn * pow2(f.ex); b.fsc = b.cn * pow2(b.ex);
-                    if (Xw[q]) { Xw[q][0] = 0.0; Xw[q][Nl - 1] = 0.0; }
-                }
-                // forward: row 0 (x = 0, w' = 1), then the ordinary step to row 1
-                coef(f0, th0[q], g, C, Fv);
-                f.x = 0.0; f.w = 1.0; f.gp = g; f.gpp = g;
-                out_step<+1, WRITE>(f, f1, th0[q], lam[q], 1, Nl, false, Xw[q]);
-                // backward: row N-1 (x = 0), row M = N-2 with x = 1, w' = -a_M
-                coef(b0, th0[q], g, C, Fv);
-                const double gN = g;
-                coef(b1, th0[q], g, C, Fv);
-                const double a = g + gN;
-                b.x = 1.0; b.w = -a; b.gp = g; b.gpp = gN; b.tcur = fma(-lam[q], Fv, C);
-                if (WRITE) { if (Xw[q]) Xw[q][Nl - 2] = norm_value(1.0, b.fsc); }
-                else {
-                    b.bad |= not_pos_normal(a) | not_pos_normal(Fv) | not_finite(C);
-                    b.a0o = b.tcur; b.a1o = Fv; b.vmax = 1.0; b.jmax = Nl - 2;
-                    b.W1 = 1.0;
-                }
+        for (int q = 0; q < SPL; ++q) {
+            double g, C, Fv;
+            Sweep& f = F_[q]; Sweep& b = B_[q];
+            sweep_zero(f); sweep_zero(b);
+            if (WRITE) {
+                const bool ok = !out[q].bad && out[q].zmax > 0.0 && out[q].zmax < 1e300;
+                f.cn = ok ? NORM_INFLATE / (out[q].xkf * out[q].zmax) : 0.0;
+                b.cn = ok ? NORM_INFLATE / (out[q].xkb * out[q].zmax) : 0.0;
+                f.ex = -out[q].Ekf; b.ex = -out[q].Ekb;
+                f.fsc = f.cn * pow2(f.ex); b.fsc = b.cn * pow2(b.ex);
+                if (Xw[q]) { Xw[q][0] = 0.0; Xw[q][Nl - 1] = 0.0; }
             }
-            i0 = 2;
-            if (TR - 1 < qmin) {
-                // rows 2 and 3 (and N-3, N-4) have their own stencils: general step; the rest of the tile is pipelined
-                for (; i0 < 4; ++i0) {
-                    const Rec rf = load_rec(ctx.frec(i0)), rb = load_rec(ctx.brec(i0));
-#pragma unroll
-                    for (int q = 0; q < SPL; ++q) {
-                        out_step<+1, WRITE>(F_[q], rf, th0[q], lam[q], i0, Nl, false, Xw[q]);
-                        out_step<-1, WRITE>(B_[q], rb, th0[q], lam[q], i0, Nl, false, Xw[q]);
-                    }
-                }
+            // forward: row 0 (x = 0, w' = 1), then the ordinary step to row 1
+            coef(f0, th0[q], g, C, Fv);
+            f.x = 0.0; f.w = 1.0; f.gp = g; f.gpp = g;
+            out_step<+1, WRITE>(f, f1, th0[q], lam[q], 1, Nl, false, Xw[q]);
+            // backward: row N-1 (x = 0), row M = N-2 with x = 1, w' = -a_M
+            coef(b0, th0[q], g, C, Fv);
+            const double gN = g;
+            coef(b1, th0[q], g, C, Fv);
+            const double a = g + gN;
+            b.x = 1.0; b.w = -a; b.gp = g; b.gpp = gN; b.tcur = fma(-lam[q], Fv, C);
+            if (WRITE) { if (Xw[q]) Xw[q][Nl - 2] = norm_value(1.0, b.fsc); }
+            else {
+                b.bad |= not_pos_normal(a) | not_pos_normal(Fv) | not_finite(C);
+                b.a0o = b.tcur; b.a1o = Fv; b.vmax = 1.0; b.jmax = Nl - 2;
+                b.W1 = 1.0;
             }
         }
-        if (TR * s + TR - 1 < qmin) {
-            // fast path (pipelined, interior rows): coefficients one step ahead, records two steps ahead; i0 is even
-            const int q0 = TR * s;
-            OCo cf[SPL], cb[SPL];
-            {
-                const Rec f0 = load_rec(ctx.frec(i0)), b0 = load_rec(ctx.brec(i0));
-#pragma unroll
-                for (int q = 0; q < SPL; ++q) {
-                    out_coef<WRITE>(f0, th0[q], lam[q], F_[q].gp, cf[q], F_[q].bad);
-                    out_coef<WRITE>(b0, th0[q], lam[q], B_[q].gp, cb[q], B_[q].bad);
-                }
-            }
-            Rec rf = load_rec(ctx.frec(i0 + 1)), rb = load_rec(ctx.brec(i0 + 1));
-#pragma unroll 1
-            for (int i = i0; i < TR - 2; i += 2) {
-                const Rec nf = load_rec(ctx.frec(i + 2)), nb = load_rec(ctx.brec(i + 2));
-#pragma unroll
-                for (int q = 0; q < SPL; ++q)
-                    out_joint<0, WRITE>(rf, rb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], q0 + i, Nl, Xw[q]);
-                rf = load_rec(ctx.frec(i + 3)); rb = load_rec(ctx.brec(i + 3));
-#pragma unroll
-                for (int q = 0; q < SPL; ++q)
-                    out_joint<1, WRITE>(nf, nb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], q0 + i + 1, Nl, Xw[q]);
-                if (i == EBLK - 2) rescale_all(true, true);
-            }
+    }
+    int s_next = 0, i_first = 2;
+    if (nfs > 0) {
+        // rows 2 and 3 (and N-3, N-4) have their own stencils, rows 4 and 5 bring the pipeline to a step = 2 (mod 4):
+        // general steps
+        for (int i = 2; i < 6; ++i) {
+            const Rec rf = load_rec(ctx.frec(i)), rb = load_rec(ctx.brec(i));
 #pragma unroll
             for (int q = 0; q < SPL; ++q) {
-                // step 30 (its successor's coefficients from the record of step 31), then step 31 on its own
-                out_joint<0, WRITE>(rf, rb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], q0 + TR - 2, Nl, Xw[q]);
-                out_chain_tail<+1, 1, WRITE>(F_[q], cf[q], q0 + TR - 1, Xw[q]);
-                out_chain_tail<-1, 1, WRITE>(B_[q], cb[q], Nl - 1 - (q0 + TR - 1), Xw[q]);
+                out_step<+1, WRITE>(F_[q], rf, th0[q], lam[q], i, Nl, false, Xw[q]);
+                out_step<-1, WRITE>(B_[q], rb, th0[q], lam[q], i, Nl, false, Xw[q]);
             }
-            rescale_all(true, true);
-        } else {
+        }
+        // ---- fast region: steps 6 .. 32 nfs - 1 as ONE software pipeline across the stage boundaries (coefficients one
+        // step ahead, records two steps ahead), in blocks of four steps with no branch but the back edge (see eval_pass;
+        // four steps also let the 4-row stencil window rotate through register names instead of being moved).  A trip of
+        // the stage loop covers the steps 32 m - 2 .. 32 m + 29, whose records all lie in stage m.
+        const int gend = TR * nfs;
+        OCo cf[SPL], cb[SPL];
+        const double* pf = ctx.frec(6);
+        const double* pb = ctx.brec(6);
+        {
+            const Rec f0 = load_rec(pf), b0 = load_rec(pb);
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) {
+                out_coef<WRITE>(f0, th0[q], lam[q], F_[q].gp, cf[q], F_[q].bad);
+                out_coef<WRITE>(b0, th0[q], lam[q], B_[q].gp, cb[q], B_[q].bad);
+            }
+        }
+        pf += REC; pb -= REC;
+        Rec rf = load_rec(pf), rb = load_rec(pb);         // records of step 7
+        pf += REC; pb -= REC;                              // -> records of step 8
+        int g = 6;
+        auto blocks4 = [&](int nblk) {
 #pragma unroll 1
-            for (int i = i0; i < TR && TR * s + i <= qmax; ++i) {
-                const int qq = TR * s + i;
-                if (qq <= qf_end) {
-                    const Rec rf = load_rec(ctx.frec(i));
+            for (int b = 0; b < nblk; ++b) {
+                Rec nf = load_rec(pf), nb = load_rec(pb);
 #pragma unroll
-                    for (int q = 0; q < SPL; ++q) out_step<+1, WRITE>(F_[q], rf, th0[q], lam[q], qq, Nl, false, Xw[q]);
-                }
-                if (qq <= qb_end) {
-                    const Rec rb = load_rec(ctx.brec(i));
+                for (int q = 0; q < SPL; ++q) out_joint<0, WRITE>(rf, rb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], g, Nl, Xw[q]);
+                rf = load_rec(pf + REC); rb = load_rec(pb - REC);
 #pragma unroll
-                    for (int q = 0; q < SPL; ++q) out_step<-1, WRITE>(B_[q], rb, th0[q], lam[q], qq, Nl, qq == qb_end, Xw[q]);
-                }
-                if ((i & (EBLK - 1)) == EBLK - 1) rescale_all(qq < qf_end, qq < qb_end);       // a finished sweep keeps its final scale
+                for (int q = 0; q < SPL; ++q) out_joint<1, WRITE>(nf, nb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], g + 1, Nl, Xw[q]);
+                nf = load_rec(pf + 2 * REC); nb = load_rec(pb - 2 * REC);
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) out_joint<0, WRITE>(rf, rb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], g + 2, Nl, Xw[q]);
+                rf = load_rec(pf + 3 * REC); rb = load_rec(pb - 3 * REC);
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) out_joint<1, WRITE>(nf, nb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], g + 3, Nl, Xw[q]);
+                pf += 4 * REC; pb -= 4 * REC;
+                g += 4;
             }
+        };
+#pragma unroll 1
+        for (int m = 0; m < nfs; ++m) {
+            if (m > 0) { ctx.wait(m); pf = ctx.frec(0); pb = ctx.brec(0); }
+            blocks4(m > 0 ? 4 : 2);                        // steps 32 m - 2 (m = 0: 6) .. 32 m + 13
+            rescale_all(true, true);
+            if (m > 0) ctx.release(m - 1);
+            blocks4(4);                                    // steps 32 m + 14 .. 32 m + 29
+            rescale_all(true, true);
+        }
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) {
+            // step gend - 2 (its successor's coefficients from the record already loaded), then step gend - 1 on its own
+            out_joint<0, WRITE>(rf, rb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], gend - 2, Nl, Xw[q]);
+            out_chain_tail<+1, 1, WRITE>(F_[q], cf[q], gend - 1, Xw[q]);
+            out_chain_tail<-1, 1, WRITE>(B_[q], cb[q], Nl - 1 - (gend - 1), Xw[q]);
+        }
+        rescale_all(true, true);
+        ctx.release(nfs - 1);
+        s_next = nfs;
+        i_first = 0;
+    }
+    // ---- general steps (the first rows when there is no fast region, the ends of the sweeps, unequal sweeps)
+    for (int s = s_next; s < nst; ++s) {
+        if (s > 0) ctx.wait(s);
+#pragma unroll 1
+        for (int i = (s == s_next) ? i_first : 0; i < TR && TR * s + i <= qmax; ++i) {
+            const int qq = TR * s + i;
+            if (qq <= qf_end) {
+                const Rec rf = load_rec(ctx.frec(i));
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) out_step<+1, WRITE>(F_[q], rf, th0[q], lam[q], qq, Nl, false, Xw[q]);
+            }
+            if (qq <= qb_end) {
+                const Rec rb = load_rec(ctx.brec(i));
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) out_step<-1, WRITE>(B_[q], rb, th0[q], lam[q], qq, Nl, qq == qb_end, Xw[q]);
+            }
+            if ((i & (EBLK - 1)) == EBLK - 1) rescale_all(qq < qf_end, qq < qb_end);       // a finished sweep keeps its final scale
         }
         ctx.release(s);
     }

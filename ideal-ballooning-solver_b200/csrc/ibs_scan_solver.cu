@@ -45,7 +45,27 @@ struct ScanParams {
     double* X_rows;           // where the eigenfunctions go: X_out, or scratch when only dX is wanted (null: no eigenfunction output)
     double* shift_ws; int* info_ws;      // two-kernel form: converged shift and counters handed from the iteration kernel to the output kernel
     unsigned* counter;
+    // fused per-surface arg-max (ball_scan.py:279-295); items_per_surface = 0: off
+    int items_per_surface, lines_per_surface;
+    double* item_val; int* item_idx;       // [nitems]: best of each (line, theta0-group) item; idx = -2: the item holds a NaN
+    unsigned* surf_count;                  // [nsurf], zeroed: items of the surface that have finished
+    double* best_out; double* sigma0_out;  // [nsurf][2] packed (max, flat index as a double), [nsurf] (nullable)
 };
+
+// (value, first flat index) maximum with the tie rule of np.where(...)[k][0] (ball_scan.py:284-285): larger value wins, equal
+// values keep the smaller index; NaN is tracked separately (np.max propagates it)
+__device__ __forceinline__ void best_merge(double& bv, int& bi, double ov, int oi) {
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+}
+__device__ __forceinline__ void warp_best(double& bv, int& bi, int& anynan) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(FULL, bv, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        anynan |= __shfl_xor_sync(FULL, anynan, o);
+        best_merge(bv, bi, ov, oi);
+    }
+}
 
 // ---- device context: record streaming + warp votes --------------------------------------------------
 struct DevCtx {
@@ -200,6 +220,47 @@ scan_solve_kernel(const ScanParams p) {
                     if (p.info_out) p.info_out[sidx[q]] = res[q].info;
                 }
             }
+        if (MODE != MODE_ITER && p.items_per_surface > 0) {
+            // ---- fused arg-max: the item's best -> its slot; the LAST item of a surface to finish reduces the slots
+            const int surf = line / p.lines_per_surface;
+            double bv = -INFINITY; int bi = 0x7fffffff, anynan = 0;
+#pragma unroll
+            for (int q = 0; q < SPL; ++q)
+                if (act[q]) {
+                    const double v = res[q].gam;
+                    const int flat = (line - surf * p.lines_per_surface) * p.nth0 + grp * (32 * SPL) + q * 32 + lane;
+                    if (v != v) anynan = 1;
+                    best_merge(bv, bi, v, flat);
+                }
+            warp_best(bv, bi, anynan);
+            unsigned prev = 0;
+            if (lane == 0) {
+                p.item_val[item] = bv;
+                p.item_idx[item] = anynan ? -2 : bi;
+                __threadfence();
+                prev = atomicAdd(&p.surf_count[surf], 1u);
+            }
+            prev = __shfl_sync(FULL, prev, 0);
+            if (prev == (unsigned)p.items_per_surface - 1u) {
+                __threadfence();
+                bv = -INFINITY; bi = 0x7fffffff; anynan = 0;
+                const int i0 = surf * p.items_per_surface;
+                for (int i = lane; i < p.items_per_surface; i += 32) {
+                    const double v = __ldcg(p.item_val + i0 + i);
+                    const int k = __ldcg(p.item_idx + i0 + i);
+                    if (k == -2) anynan = 1; else best_merge(bv, bi, v, k);
+                }
+                warp_best(bv, bi, anynan);
+                if (lane == 0) {
+                    double val, idx, sg;
+                    if (anynan) { val = __longlong_as_double(0x7ff8000000000000LL); idx = -2.0; sg = 0.05; }     // np.max propagates NaN
+                    else if (bv == 0.0) { val = bv; idx = -1.0; sg = 0.05; }                                      // ball_scan.py:279-282
+                    else { val = bv; idx = (double)bi; sg = 1.3 * fabs(bv) + 0.05; }                              // ball_scan.py:283-295
+                    p.best_out[2 * surf] = val; p.best_out[2 * surf + 1] = idx;
+                    if (p.sigma0_out) p.sigma0_out[surf] = sg;
+                }
+            }
+        }
     }
 }
 
@@ -321,36 +382,51 @@ static int scan_solve_lines(const SolveParams& p, int l0, int nline, int spl, bo
     const int nlev = num_levels(N);
     const int rows_total = level_offset(N, nlev + 1);
     const size_t v0 = (size_t)l0 * p.nth0, nsolve = (size_t)nline * p.nth0;
-    const size_t poly_bytes = (size_t)nline * rows_total * REC * sizeof(double);
-    const size_t bounds_off = (poly_bytes + 255) & ~(size_t)255;
-    const size_t counter_off = bounds_off + (((size_t)nline * 2 * sizeof(double) + 255) & ~(size_t)255);
-    const size_t hand_off = counter_off + 256;
-    const size_t hand_bytes = two ? (((nsolve * (sizeof(double) + sizeof(int))) + 255) & ~(size_t)255) : 0;
-    const size_t xs_off = hand_off + hand_bytes;
+    const int groups = (p.nth0 + 32 * spl - 1) / (32 * spl);
+    const int nitems = nline * groups;
+    const bool fused = p.lines_per_surface > 0 && p.best_out;
+    const int nsurf = fused ? nline / p.lines_per_surface : 0;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_poly = take((size_t)nline * rows_total * REC * sizeof(double));
+    const size_t o_bounds = take((size_t)nline * 2 * sizeof(double));
+    const size_t o_zero = take((2 + (size_t)nsurf) * sizeof(unsigned));             // work counters + per-surface counters: zeroed together
+    const size_t o_hand = take(two ? nsolve * (sizeof(double) + sizeof(int)) : 0);
+    const size_t o_ival = take(fused ? (size_t)nitems * sizeof(double) : 0);
+    const size_t o_iidx = take(fused ? (size_t)nitems * sizeof(int) : 0);
     const size_t xs_bytes = (p.dX_out && !p.X_out) ? nsolve * N * sizeof(double) : 0;      // X is the scratch dX is formed from
+    const size_t o_xs = take(xs_bytes);
     char* ws = nullptr;
-    IBS_CUDA_CHECK(cudaMallocAsync((void**)&ws, xs_off + xs_bytes + 256, stream));
+    IBS_CUDA_CHECK(cudaMallocAsync((void**)&ws, off + 256, stream));
     int rc = IBS_OK;
     ScanParams sp;
-    sp.poly = (double*)ws; sp.bounds = (double*)(ws + bounds_off); sp.counter = (unsigned*)(ws + counter_off);
+    sp.poly = (double*)(ws + o_poly); sp.bounds = (double*)(ws + o_bounds); sp.counter = (unsigned*)(ws + o_zero);
     sp.theta0 = p.theta0 + v0; sp.sigma = p.sigma ? p.sigma + v0 : nullptr;
     sp.nline = nline; sp.nth0 = p.nth0; sp.N = N; sp.nlev = nlev; sp.rows_total = rows_total;
-    sp.groups = (p.nth0 + 32 * spl - 1) / (32 * spl);
-    sp.nitems = nline * sp.groups;
+    sp.groups = groups;
+    sp.nitems = nitems;
     sp.h = p.h;
     sp.lam_out = p.lam_out + v0;
     sp.lam_matrix_out = p.lam_matrix_out ? p.lam_matrix_out + v0 : nullptr;
     sp.X_out = p.X_out ? p.X_out + v0 * N : nullptr;
     sp.dX_out = p.dX_out ? p.dX_out + v0 * N : nullptr;
     sp.info_out = p.info_out ? p.info_out + v0 : nullptr;
-    sp.X_rows = sp.X_out ? sp.X_out : (xs_bytes ? (double*)(ws + xs_off) : nullptr);
-    sp.shift_ws = two ? (double*)(ws + hand_off) : nullptr;
-    sp.info_ws = two ? (int*)(ws + hand_off + nsolve * sizeof(double)) : nullptr;
-    if (cudaMemsetAsync(sp.counter, 0, 2 * sizeof(unsigned), stream) != cudaSuccess) rc = IBS_ERR_CUDA;
+    sp.X_rows = sp.X_out ? sp.X_out : (xs_bytes ? (double*)(ws + o_xs) : nullptr);
+    sp.shift_ws = two ? (double*)(ws + o_hand) : nullptr;
+    sp.info_ws = two ? (int*)(ws + o_hand + nsolve * sizeof(double)) : nullptr;
+    sp.items_per_surface = fused ? p.lines_per_surface * groups : 0;
+    sp.lines_per_surface = fused ? p.lines_per_surface : 1;
+    sp.item_val = (double*)(ws + o_ival); sp.item_idx = (int*)(ws + o_iidx);
+    sp.surf_count = sp.counter + 2;
+    const size_t surf0 = fused ? (size_t)l0 / p.lines_per_surface : 0;
+    sp.best_out = fused ? p.best_out + 2 * surf0 : nullptr;
+    sp.sigma0_out = (fused && p.sigma0_out) ? p.sigma0_out + surf0 : nullptr;
+    if (cudaError_t e = cudaMemsetAsync(sp.counter, 0, (2 + (size_t)nsurf) * sizeof(unsigned), stream); e != cudaSuccess)
+        rc = cuda_fail(e, "cudaMemsetAsync(scan counters)");
     if (rc == IBS_OK) {
         scan_prep_kernel<<<nline, PREP_T, 0, stream>>>(p.base + (size_t)l0 * IBS_NBASE * N, p.dPdrho + l0, sp.theta0, p.nth0, N, p.h * p.h, nlev,
-                                                       rows_total, (double*)ws, (double*)(ws + bounds_off));
-        if (cudaGetLastError() != cudaSuccess) { set_error("scan_prep_kernel launch failed"); rc = IBS_ERR_CUDA; }
+                                                       rows_total, (double*)(ws + o_poly), (double*)(ws + o_bounds));
+        if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) rc = cuda_fail(e, "scan_prep_kernel launch");
     }
     if (rc == IBS_OK) {
         if (two && spl == 1) {
@@ -379,6 +455,11 @@ int scan_solve_dispatch(const SolveParams& p, cudaStream_t stream) {
     const size_t per_line = (size_t)level_offset(p.N, num_levels(p.N) + 1) * REC * sizeof(double) + 64;
     long long chunk = (long long)((ws_mb << 20) / per_line);
     if (chunk < 1) chunk = 1;
+    if (p.lines_per_surface > 0 && p.best_out) {           // fused arg-max: a chunk holds whole surfaces
+        IBS_REQUIRE(nline % p.lines_per_surface == 0, "nline must be a multiple of lines_per_surface");
+        chunk = (chunk / p.lines_per_surface) * p.lines_per_surface;
+        if (chunk < p.lines_per_surface) chunk = p.lines_per_surface;
+    }
     int rc = IBS_OK;
     for (long long l0 = 0; l0 < nline && rc == IBS_OK; l0 += chunk)
         rc = scan_solve_lines(p, (int)l0, (int)((nline - l0 < chunk) ? (nline - l0) : chunk), spl, two, stream);

@@ -44,6 +44,29 @@ def grid_spacing(theta) -> float:
     return float(np.diff(half)[2]) if len(theta) > 3 else float(tu[1] - tu[0])
 
 
+def fp64_peak_tflops(device=None, iters: int = 2000, reps: int = 5) -> float:
+    """Measured FP64 FMA peak of the device in TFLOP/s (2 flops per FMA): the library's DFMA-chain probe timed with CUDA
+    events, best of ``reps``.  Denominator of the FP64-pipe rooflines in ``bench.py``."""
+    import ctypes
+    _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    with torch.cuda.device(dev):
+        nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+        scratch = torch.empty(4 * nsm * 256, dtype=torch.float64, device=dev)
+        nfma = ctypes.c_double(0.0)
+        best = float("inf")
+        for _ in range(reps + 1):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(lib.ibs_fp64_probe(int(iters), scratch.data_ptr(), scratch.numel(), ctypes.byref(nfma), _stream()),
+                       "ibs_fp64_probe")
+            b.record()
+            b.synchronize()
+            best = min(best, a.elapsed_time(b))
+    return 2.0 * nfma.value / (best * 1e-3) / 1e12
+
+
 # ---------------------------------------------------------------------------------------------
 @dataclasses.dataclass
 class DeviceTables:
@@ -295,11 +318,45 @@ def scan_argmax(gamma):
     return val, idx, sig
 
 
-def scan_host(st: SurfaceTables, alpha, theta0, theta, want_xbest: bool = False, out=None):
+def scan_solve_argmax(base, dPdrho, theta0, h: float, nth0: int, lines_per_surface: int, sigma=None, want_X=False,
+                      want_dX=False, chain_len: int = 1, best_out: Optional[torch.Tensor] = None):
+    """The coarse scan of ``ball_scan.py:248-295`` in one call: K2+K3 for ``nline x nth0`` solves (theta0 fastest) with
+    the guarded per-surface arg-max fused into the solver kernel.  Returns ``(Solution, best, sigma0)``;
+    ``best`` is ``(nsurf, 2)`` = packed ``(max, flat index as a double; -1 = all-zero guard)`` -- pass a slice of a
+    preallocated gather buffer as ``best_out`` and it IS the send slot of the all-gather."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    dev = base.device
+    N = base.shape[-1]
+    base = _f64(base, dev, "base").reshape(-1, NBASE, N)
+    nline = base.shape[0]
+    dP = _f64(dPdrho, dev, "dPdrho").reshape(-1)
+    theta0 = _f64(theta0, dev, "theta0").reshape(-1)
+    n = nline * int(nth0)
+    if theta0.numel() != n or nline % int(lines_per_surface):
+        raise ValueError("theta0 must hold nline * nth0 values and nline must be a multiple of lines_per_surface")
+    nsurf = nline // int(lines_per_surface)
+    sigma = None if sigma is None else _f64(sigma, dev, "sigma")
+    lam, _, X, dX, info = _alloc_out(n, N, dev, want_X, want_dX, False)
+    if best_out is None:
+        best_out = torch.empty((nsurf, 2), dtype=torch.float64, device=dev)
+    elif best_out.dtype != torch.float64 or best_out.numel() != 2 * nsurf or not best_out.is_contiguous():
+        raise ValueError("best_out must be a contiguous float64 tensor of shape (nsurf, 2)")
+    sig0 = torch.empty((nsurf,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.ibs_scan_solve_argmax(_ptr(base), _ptr(dP), _ptr(theta0), int(nth0), nline, int(lines_per_surface), N,
+                                       float(h), _ptr(sigma), int(chain_len), _ptr(lam), _ptr(X), _ptr(dX), _ptr(info),
+                                       _ptr(best_out), _ptr(sig0), _stream())
+    _lib.check(rc, "ibs_scan_solve_argmax")
+    return Solution(lam, None, X, dX, info), best_out, sig0
+
+
+def scan_host(st: SurfaceTables, alpha, theta0, theta, want_xbest: bool = False, out=None, want_xall: bool = False):
     """End-to-end coarse scan with HOST (numpy) buffers through ``ibs_scan_host``: H2D of the tables,
-    K1 + K3 + arg-max, D2H of the results.  Returns ``(gamma (ns, nalpha, nth0), val, idx, sigma0, nbad)``
-    (+ ``xbest (ns, nl)``, the eigenfunction at each surface's maximum, when ``want_xbest``).  ``out`` may
-    carry preallocated (e.g. pinned) result arrays ``dict(gamma=, val=, idx=, sigma0=, xbest=)``."""
+    K1 + K3 (fused arg-max), D2H of the results.  Returns ``(gamma (ns, nalpha, nth0), val, idx, sigma0, nbad)``
+    (+ ``xbest (ns, nl)``, the eigenfunction at each surface's maximum, when ``want_xbest``; + ``xall
+    (ns, nalpha, nth0, nl)``, the eigenfunction of EVERY solve, when ``want_xall``).  ``out`` may carry
+    preallocated (e.g. pinned) result arrays ``dict(gamma=, val=, idx=, sigma0=, xbest=, xall=)``."""
     _lib.require_cuda()
     lib = _lib.load()
     c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -312,17 +369,22 @@ def scan_host(st: SurfaceTables, alpha, theta0, theta, want_xbest: bool = False,
     val = out.get("val") if out.get("val") is not None else np.empty(ns)
     sig = out.get("sigma0") if out.get("sigma0") is not None else np.empty(ns)
     idx = out.get("idx") if out.get("idx") is not None else np.empty(ns, dtype=np.int32)
-    xbest = None
+    xbest = xall = None
     if want_xbest:
         xbest = out.get("xbest") if out.get("xbest") is not None else np.empty((ns, nl))
+    if want_xall:
+        xall = out.get("xall") if out.get("xall") is not None else np.empty((ns, na, nt, nl))
     import ctypes
     nbad = ctypes.c_int(0)
     p = lambda a: a.ctypes.data
     rc = lib.ibs_scan_host(p(tab_mn), p(tab_nyq), p(scal), p(xm), p(xn), p(xmq), p(xnq), ns, len(xm), len(xmq),
                            float(st.phiedge), float(st.Aminor_p), p(alpha), na, p(theta0), nt, p(theta), nl,
                            grid_spacing(theta), p(gamma), p(val), p(idx), p(sig),
-                           None if xbest is None else p(xbest), ctypes.addressof(nbad))
+                           None if xbest is None else p(xbest), None if xall is None else p(xall), ctypes.addressof(nbad))
     _lib.check(rc, "ibs_scan_host")
+    res = (gamma, val, idx, sig, nbad.value)
     if want_xbest:
-        return gamma, val, idx, sig, nbad.value, xbest
-    return gamma, val, idx, sig, nbad.value
+        res = res + (xbest,)
+    if want_xall:
+        res = res + (xall,)
+    return res

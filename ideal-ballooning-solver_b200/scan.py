@@ -61,7 +61,7 @@ class ScanResult:
 
 
 def coarse_scan(tables: engine.DeviceTables, alpha, theta0, theta, want_X: bool = False,
-                lam0=None) -> ScanResult:
+                lam0=None, best_out: Optional[torch.Tensor] = None) -> ScanResult:
     """Coarse (alpha, theta0) grid of every surface in ``tables`` (``ball_scan.py:248-295``): K1 for
     ``ns x nalpha`` field lines, K2+K3 for ``ns x nalpha x nth0`` solves, guarded arg-max."""
     dev = tables.tab_mn.device
@@ -71,10 +71,19 @@ def coarse_scan(tables: engine.DeviceTables, alpha, theta0, theta, want_X: bool 
     geo = engine.geometry_batch(tables, alpha_t, theta_np)
     ns, na, nt = tables.ns, alpha_t.shape[-1], theta0_t.numel()
     th0 = theta0_t.repeat(ns * na)
-    sol = engine.solve_base_batch(geo.base, geo.dPdrho, th0, engine.grid_spacing(theta_np), nth0=nt, lam0=lam0,
-                                  want_X=want_X, want_dX=False, want_matrix=False, chain_len=chain_length(nt))
-    gamma = sol.lam.reshape(ns, na, nt)
-    val, idx, sig = engine.scan_argmax(gamma)
+    if lam0 is None:
+        sol, best, sig = engine.scan_solve_argmax(geo.base, geo.dPdrho, th0, engine.grid_spacing(theta_np), nt, na, want_X=want_X,
+                                                  chain_len=chain_length(nt), best_out=best_out)
+        gamma = sol.lam.reshape(ns, na, nt)
+        val, idx = best[:, 0], best[:, 1].to(torch.int32)
+    else:
+        sol = engine.solve_base_batch(geo.base, geo.dPdrho, th0, engine.grid_spacing(theta_np), nth0=nt, lam0=lam0,
+                                      want_X=want_X, want_dX=False, want_matrix=False, chain_len=chain_length(nt))
+        gamma = sol.lam.reshape(ns, na, nt)
+        val, idx, sig = engine.scan_argmax(gamma)
+        if best_out is not None:
+            best_out[:, 0] = val
+            best_out[:, 1] = idx.to(torch.float64)
     safe = idx.clamp(min=0).long()
     ia, it = safe // nt, safe % nt
     if alpha_t.dim() == 2:
@@ -89,26 +98,51 @@ def coarse_scan(tables: engine.DeviceTables, alpha, theta0, theta, want_X: bool 
     return ScanResult(gamma, val, idx, sig, a_guess, t_guess, X, sol.info, geo)
 
 
+class SurfaceGather:
+    """The one exchange step of the scan (replaces the three ``MPI.Gather`` of ``ball_scan.py:345-347``) with NO kernel
+    but the collective itself: the solver writes each local surface's packed ``(max, index)`` pair straight into this
+    object's send slot (``engine.scan_solve_argmax(..., best_out=g.send)``), and ``g.exchange()`` is one
+    ``all_gather_into_tensor`` into a preallocated ``(world, nmax, 2)`` buffer.  Works with NCCL (GPU tensors) and gloo
+    (CPU tensors).  Ranks own contiguous blocks of surfaces (``shard_range``); shorter blocks leave their tail rows unused."""
+
+    def __init__(self, ns_total: int, device, group=None):
+        import torch.distributed as dist
+        self.group = group
+        self.dist = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.dist else 1
+        self.rank = dist.get_rank(group) if self.dist else 0
+        self.sizes = [shard_range(ns_total, r, self.world) for r in range(self.world)]
+        self.nmax = max(1, max(hi - lo for lo, hi in self.sizes))
+        lo, hi = self.sizes[self.rank]
+        self.nlocal = hi - lo
+        self.recv = torch.zeros((self.world, self.nmax, 2), dtype=torch.float64, device=device)
+        self._send_full = self.recv[self.rank] if not self.dist else torch.zeros((self.nmax, 2), dtype=torch.float64, device=device)
+        self.send = self._send_full[: self.nlocal]          # (nlocal, 2) contiguous view: the solver's best_out
+
+    def exchange(self) -> torch.Tensor:
+        """All-gather the send slots; returns the ``(world, nmax, 2)`` buffer (no copy, no cast)."""
+        if self.dist:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.recv.view(-1), self._send_full.view(-1), group=self.group)
+        return self.recv
+
+    def unpack(self):
+        """``(val (ns_total,), idx (ns_total,) int32)`` in surface order (host-side convenience, not on the timed path)."""
+        vals = torch.cat([self.recv[r, : hi - lo, 0] for r, (lo, hi) in enumerate(self.sizes)])
+        idxs = torch.cat([self.recv[r, : hi - lo, 1] for r, (lo, hi) in enumerate(self.sizes)]).to(torch.int32)
+        return vals, idxs
+
+
 def gather_surface_maxima(val: torch.Tensor, idx: torch.Tensor, ns_total: int, group=None):
-    """The one exchange step of the scan (replaces the three ``MPI.Gather`` of ``ball_scan.py:345-347``):
-    all-gather the per-surface ``(val, idx)`` pairs of every rank's contiguous block of surfaces.  Works
-    with NCCL (GPU tensors) and gloo (CPU tensors)."""
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    """All-gather per-surface ``(val, idx)`` pairs of every rank's contiguous block of surfaces (convenience form on
+    separate arrays; the scan itself uses ``SurfaceGather``, whose send slot the solver kernel fills directly)."""
+    g = SurfaceGather(ns_total, val.device, group)
+    if g.world == 1:
         return val, idx
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    sizes = [shard_range(ns_total, r, world) for r in range(world)]
-    nmax = max(hi - lo for lo, hi in sizes)
-    packed = torch.zeros((nmax, 2), dtype=torch.float64, device=val.device)
-    lo, hi = sizes[rank]
-    packed[: hi - lo, 0] = val
-    packed[: hi - lo, 1] = idx.to(torch.float64)
-    out = [torch.empty_like(packed) for _ in range(world)]
-    dist.all_gather(out, packed, group=group)
-    vals = torch.cat([o[: h - l, 0] for o, (l, h) in zip(out, sizes)])
-    idxs = torch.cat([o[: h - l, 1] for o, (l, h) in zip(out, sizes)]).to(torch.int32)
-    return vals, idxs
+    g.send[:, 0] = val
+    g.send[:, 1] = idx.to(torch.float64)
+    g.exchange()
+    return g.unpack()
 
 
 def sharded_coarse_scan(st: SurfaceTables, alpha, theta0, theta, device=None, want_X=False, group=None):
@@ -122,16 +156,14 @@ def sharded_coarse_scan(st: SurfaceTables, alpha, theta0, theta, device=None, wa
         rank, world = 0, 1
     lo, hi = shard_range(st.ns, rank, world)
     device = device or torch.device("cuda", torch.cuda.current_device())
+    gather = SurfaceGather(st.ns, device, group)
+    res = None
     if hi > lo:
         dt = engine.DeviceTables.from_host(st.select(np.arange(lo, hi)), device)
-        res = coarse_scan(dt, alpha, theta0, theta, want_X=want_X)
-        val, idx = res.val, res.idx
-    else:
-        # more ranks than surfaces: this rank has nothing to scan but still takes part in the exchange
-        res = None
-        val = torch.empty((0,), dtype=torch.float64, device=device)
-        idx = torch.empty((0,), dtype=torch.int32, device=device)
-    val_all, idx_all = gather_surface_maxima(val, idx, st.ns, group)
+        res = coarse_scan(dt, alpha, theta0, theta, want_X=want_X, best_out=gather.send)
+    # (more ranks than surfaces: a rank with nothing to scan still takes part in the exchange)
+    gather.exchange()
+    val_all, idx_all = gather.unpack()
     return res, (lo, hi), val_all, idx_all
 
 

@@ -60,6 +60,11 @@ const char* ibs_last_error(void);
 /* number of SMs / compute capability of the current device (0 on success) */
 int ibs_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Measurement aid (bench.py): launches independent DFMA chains on every SM (32 warps per SM, 8 chains per thread) so
+ * that the caller can time the device's FP64 FMA peak with CUDA events -- the denominator of the FP64-pipe rooflines of
+ * K1 and K2+K3.  scratch [>= 4 * SMs * 256] doubles (device); *fma_count_out (host) = FMAs one launch executes.       */
+int ibs_fp64_probe(int iters, double* scratch, long long scratch_len, double* fma_count_out, void* stream);
+
 /* ---- K1: field-line geometry ------------------------------------------------------------------
  * Batched vmec_fieldlines(vs, s, alpha, theta1d=theta) (utils.py:161-864) restricted to the eight
  * arrays the ballooning path reads, for ns surfaces x nalpha field lines x nl points:
@@ -151,6 +156,18 @@ int ibs_obj_w_grad_batch(const double* base3, const double* dPdrho3, const doubl
 int ibs_scan_argmax(const double* gamma, int ns, int ngrid, double* val_out, int* idx_out,
                     double* sigma0_out, void* stream);
 
+/* The coarse scan of ball_scan.py:248-295 in ONE call: K2+K3 for nline field lines x nth0 theta0 (theta0 fastest;
+ * theta0 [nline*nth0]) with the guarded per-surface arg-max fused into the solver kernel's epilogue (no separate
+ * launch): lines_per_surface consecutive field lines form one surface.
+ *   best_out [nline/lines_per_surface][2]: packed (max, flat (line-in-surface, theta0) index as a double; -1 = the
+ *          all-zero guard, -2 = NaN) -- laid out so that it can BE the send slot of the one all-gather that replaces
+ *          the three MPI.Gather of ball_scan.py:345-347;  sigma0_out [nsurf] or NULL;
+ *   lam_out [nline*nth0]; X_out, dX_out [nline*nth0][N] or NULL; info_out or NULL; sigma, chain_len as above.       */
+int ibs_scan_solve_argmax(const double* base, const double* dPdrho, const double* theta0, int nth0, int nline,
+                          int lines_per_surface, int N, double h, const double* sigma, int chain_len,
+                          double* lam_out, double* X_out, double* dX_out, int* info_out,
+                          double* best_out, double* sigma0_out, void* stream);
+
 /* ---- marginal-stability classifier ---------------------------------------------------------------
  * Sturm/Newcomb node count of the discretised ballooning operator at a given lam (the s-alpha test
  * of the reference shoots at lam = 0, tests/shifted-circle-s-alpha/bishop_ball_s-alpha.py:90-115):
@@ -160,16 +177,18 @@ int ibs_count_above_batch(const double* g, const double* c, const double* f, int
 
 /* ---- end-to-end host entry point -----------------------------------------------------------------
  * Coarse scan of ball_scan.py:248-295 for ns surfaces with HOST buffers: copies the tables to the
- * device, runs K1 (ns x nalpha lines), K3 (ns x nalpha x nth0 solves) and the arg-max, and copies
- * gamma [ns][nalpha][nth0], the per-surface (val, idx, sigma0) and (if xbest_out != NULL) the
- * eigenfunction X [ns][nl] of each surface's arg-max solve back.  Synchronous.                     */
+ * device, runs K1 (ns x nalpha lines) and K2+K3 with the fused arg-max (ns x nalpha x nth0 solves), and
+ * copies gamma [ns][nalpha][nth0], the per-surface (val, idx, sigma0) and the eigenfunctions back:
+ *   xbest_out [ns][nl] or NULL: X of each surface's arg-max solve (what ball_scan.py keeps, :322-339);
+ *   xall_out  [ns][nalpha][nth0][nl] or NULL: X of EVERY solve (8 nl bytes per solve over PCIe).
+ * Synchronous; uploads, kernels and downloads of consecutive chunks of surfaces overlap.            */
 int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* scal,
                   const double* xm, const double* xn, const double* xm_nyq, const double* xn_nyq,
                   int ns, int mnmax, int mnmax_nyq, double phiedge, double aminor_p,
                   const double* alpha, int nalpha, const double* theta0, int nth0,
                   const double* theta, int nl, double h,
                   double* gamma_out, double* val_out, int* idx_out, double* sigma0_out, double* xbest_out,
-                  int* nbad_out);
+                  double* xall_out, int* nbad_out);
 
 #ifdef __cplusplus
 }

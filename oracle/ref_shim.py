@@ -4,9 +4,10 @@ This module makes ``/root/reference/utils.py`` importable in THIS container so
 that (a) the numpy restatement in ``oracle/ballooning_oracle.py`` can be
 validated against the real thing and (b) golden vectors can be generated
 (``tests/golden/make_golden.py``).  ``/root/reference`` does not exist on the
-GPU box, so nothing that runs there (``-m gpu`` tests, ``smoke()``,
-``bench.py``) may import this file; they use the committed fixtures and the
-restatement instead.
+GPU box; there the only copy of the reference is ``oracle/_ref/utils.py`` (made
+byte for byte by ``oracle/make_ref.py``, git-ignored), which ``bench.py``'s CPU
+arm times as the real reference.  The ``-m gpu`` tests and ``smoke()`` use the
+committed fixtures and the restatement, not this file.
 
 Nothing under ``oracle/`` is product code: only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / reference arm may
@@ -33,7 +34,22 @@ import warnings
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("IBS_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference_root():
+    """``$IBS_REFERENCE_ROOT``, else ``/root/reference`` (build container), else ``oracle/_ref`` (the byte-for-byte copy of
+    ``utils.py`` made by ``oracle/make_ref.py``; the only form in which the reference exists on the GPU box)."""
+    env = os.environ.get("IBS_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isfile(os.path.join(cand, "utils.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 _TABLES_2D = ["rmnc", "zmns", "lmns", "gmnc", "bmnc", "bsupumnc", "bsupvmnc",
               "bsubsmns", "bsubumnc", "bsubvmnc"]

@@ -117,3 +117,79 @@ def test_hberg_full_resolution(cuda_lib):
     engine, geo, th0, theta, shape = _setup("hberg", ns_cap=32)
     sol = _check_properties(engine, geo, th0, theta, shape, sample=512, chain=1)
     assert sol.lam.numel() == 32 * 64
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Direct parity with the oracle AT FULL SIZE: sampled solves of every configuration against the LAPACK tridiagonal route of
+# the restated gamma_ball_full (oracle `method="lambda_max"`: O(N) per solve, so N = 1025 / 2049 / 8193 finish in seconds).
+# ---------------------------------------------------------------------------------------------------------------
+def _oracle_sample(geo, th0, theta, shape, sol, nsample=64, seed=5):
+    from oracle import ballooning_oracle as bo
+    from helpers import LAM_RTOL, X_ATOL
+    from ideal_ballooning_solver_b200.engine import BASE_NAMES
+    ns, na, nt = shape
+    n = ns * na * nt
+    rng = np.random.default_rng(seed)
+    pick = np.unique(np.concatenate([[0, n - 1], rng.integers(0, n, nsample - 2)]))
+    base = geo.base.reshape(ns * na, len(BASE_NAMES), -1)
+    dP = geo.dPdrho.reshape(-1).cpu().numpy()
+    th0_h = th0.cpu().numpy()
+    lam_d, X_d = sol.lam.cpu().numpy(), sol.X
+    row = {nm: k for k, nm in enumerate(BASE_NAMES)}
+    worst_l = worst_x = 0.0
+    for i in pick:
+        line = i // nt
+        b = base[line].cpu().numpy()
+        t0 = th0_h[i]
+        cv = b[row["cvdrift"]] + t0 * b[row["cvdrift0"]]                                     # ball_scan.py:267-268
+        gd = b[row["gds2"]] + 2 * t0 * b[row["gds21"]] + t0 ** 2 * b[row["gds22"]]
+        info = {}
+        lam, X, *_ = bo.gamma_ball_full(dP[line], theta, b[row["bmag"]], b[row["gradpar_theta_pest"]], cv, gd,
+                                        method="lambda_max", info=info)
+        Xs = X * np.sign(X[np.argmax(np.abs(X))])
+        worst_l = max(worst_l, abs(lam_d[i] - lam) / abs(lam))
+        # eigenvector conditioning: eps ||S|| / gap; the 1e-8 bar applies where the gap allows it
+        if info["gap"] > 1e-6:
+            worst_x = max(worst_x, float(np.max(np.abs(X_d[i].cpu().numpy() - Xs))))
+    assert worst_l < LAM_RTOL, worst_l
+    assert worst_x < X_ATOL, worst_x
+    return len(pick)
+
+
+@pytest.mark.parametrize("name,ns_cap", [("d3d", None), ("ncsx", None), ("hberg", 64)])
+def test_full_config_samples_match_oracle(cuda_lib, name, ns_cap):
+    """64 sampled solves of each BASELINE scan configuration against the oracle: lambda to 1e-10 relative, X to 1e-8."""
+    engine, geo, th0, theta, shape = _setup(name, ns_cap=ns_cap)
+    ns, na, nt = shape
+    sol, best, sig = engine.scan_solve_argmax(geo.base, geo.dPdrho, th0, engine.grid_spacing(theta), nt, na, want_X=True,
+                                              chain_len=16 if nt > 1 else 1)
+    assert int((sol.flags & 3).max().item()) == 0
+    assert _oracle_sample(geo, th0, theta, shape, sol) >= 32
+    # the fused / packed arg-max against numpy on the same gamma grid (first index on ties, ball_scan.py:279-295)
+    from oracle import ballooning_oracle as bo
+    gam = sol.lam.reshape(ns, na, nt).cpu().numpy()
+    b = best.cpu().numpy()
+    for js in range(0, ns, max(1, ns // 16)):
+        ia, it, s0 = bo.argmax_with_guards(gam[js])
+        assert b[js, 0] == gam[js].max() and int(b[js, 1]) == ia * nt + it
+        assert float(sig[js].item()) == s0
+
+
+def test_hberg_all_surfaces_properties(cuda_lib):
+    """All 256 surfaces x 64 alpha of BASELINE configs[3] at ntheta = 8192 (16 384 solves of 8193 points): flags, positivity
+    and normalisation of X, and the Sturm certificate of lambda_max on a sample (the dense checks of the property test above
+    are bounded to a sample to bound memory)."""
+    import torch
+    engine, geo, th0, theta, shape = _setup("hberg")
+    ns, na, nt = shape
+    h = engine.grid_spacing(theta)
+    sol = engine.solve_base_batch(geo.base, geo.dPdrho, th0, h, nth0=nt, chain_len=1, want_dX=False)
+    assert sol.lam.numel() == 256 * 64
+    assert int((sol.flags & 3).max().item()) == 0
+    assert bool((sol.X >= 0).all()) and bool((sol.X.max(dim=1).values == 1.0).all())
+    idx = torch.linspace(0, sol.lam.numel() - 1, 256).round().long().cuda().unique()
+    ex = engine.solve_base_batch(geo.base, geo.dPdrho, th0[idx], h, line_of_solve=(idx // nt).to(torch.int32), want_gcf=True)
+    scale = ex.lam_matrix.abs().clamp_min(1e-3)
+    assert int(engine.count_above_batch(ex.g, ex.c, ex.f, h, ex.lam_matrix + 1e-9 * scale).max().item()) == 0
+    assert int(engine.count_above_batch(ex.g, ex.c, ex.f, h, ex.lam_matrix - 1e-7 * scale).min().item()) >= 1
+    assert float(((ex.lam - sol.lam[idx]).abs() / sol.lam[idx].abs()).max().item()) < 1e-11

@@ -175,3 +175,38 @@ def test_derm_dermv_facade_matches_reference_golden(golden):
     assert n == 14
     with pytest.raises(NotImplementedError):
         ra.dermv(G["a1"], G["b1"], "r")
+
+
+def test_batched_objective_failure_does_not_hang():
+    """A failing batched evaluation (CUDA error, bad input, ...) must reach EVERY waiting surface thread as an exception;
+    before the fix the failing thread left its entry pending and all the others waited forever."""
+    import threading
+    from ideal_ballooning_solver_b200 import scan
+
+    obj = scan._BatchedObjective.__new__(scan._BatchedObjective)
+    obj.cv = threading.Condition(); obj.active = set(); obj.pending = {}; obj.results = {}; obj.nbatches = 0; obj.nevals = 0
+    calls = []
+
+    def boom():
+        calls.append(sorted(obj.pending))
+        raise RuntimeError("injected batch failure")
+
+    obj._run_batch = boom
+    obj.start(range(4))
+    errs = [None] * 4
+
+    def worker(i):
+        try:
+            obj.evaluate(i, (0.1 * i, 0.2))
+        except Exception as e:      # noqa: BLE001
+            errs[i] = e
+        finally:
+            obj.finish(i)
+
+    ts = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=20)
+    assert not any(t.is_alive() for t in ts), "a surface thread is still waiting"
+    assert all(isinstance(e, RuntimeError) for e in errs) and calls == [[0, 1, 2, 3]]
