@@ -3,6 +3,7 @@
 // These are streaming reductions (HBM-bound): one CTA per (solve[, parameter]), coalesced loads,
 // warp-shuffle + shared-memory reduction.
 #include "ibs_common.cuh"
+#include "ibs_refine_core.cuh"
 
 namespace ibs {
 
@@ -221,6 +222,60 @@ int launch_best_setup(const double* best, const double* theta0, int ns, int ngri
                       int* line_out, double* th0_out, cudaStream_t st) {
     if (ns == 0) return IBS_OK;
     best_setup_kernel<<<(ns + 127) / 128, 128, 0, st>>>(best, theta0, ns, ngrid, nth0, val_out, idx_out, line_out, th0_out);
+    IBS_CUDA_CHECK(cudaGetLastError());
+    return IBS_OK;
+}
+
+// ---- batched refinement of the coarse maxima (ball_scan.py:305-314): one thread per surface -----------------------------
+// Consumes the batched obj_w_grad evaluation of every problem's trial point, advances the problems (see ibs_refine_core.cuh)
+// and writes the next trial points in the layout the evaluation takes: alphas3 [n][3] = (a - del/2, a, a + del/2)
+// (utils.py:1641-1646) and theta0 [n].
+__global__ void refine_init_kernel(double* __restrict__ state, int n, const double* __restrict__ a0, const double* __restrict__ t0,
+                                   double alo, double ahi, double tlo, double thi, double del_alpha, double* __restrict__ alphas3,
+                                   double* __restrict__ theta0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    refine::State s;
+    refine::init(s, a0[i], t0[i], alo, ahi, tlo, thi);
+    double* o = state + (size_t)i * refine::NSTATE;
+    const double* src = reinterpret_cast<const double*>(&s);
+    for (int k = 0; k < refine::NSTATE; ++k) o[k] = src[k];
+    alphas3[3 * i] = s.xt[0] - 0.5 * del_alpha; alphas3[3 * i + 1] = s.xt[0]; alphas3[3 * i + 2] = s.xt[0] + 0.5 * del_alpha;
+    theta0[i] = s.xt[1];
+}
+__global__ void refine_step_kernel(double* __restrict__ state, int n, const double* __restrict__ val, const double* __restrict__ grad,
+                                   const int* __restrict__ info, refine::Options opt, double del_alpha, double* __restrict__ alphas3,
+                                   double* __restrict__ theta0, int* __restrict__ nactive) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = false;
+    if (i < n) {
+        refine::State s;
+        double* o = state + (size_t)i * refine::NSTATE;
+        double* dst = reinterpret_cast<double*>(&s);
+        for (int k = 0; k < refine::NSTATE; ++k) dst[k] = o[k];
+        const bool failed = info && ((info[i] >> 16) & (IBS_FLAG_NOT_CONVERGED | IBS_FLAG_BAD_INPUT));
+        refine::consume(s, val[i], grad[2 * i], grad[2 * i + 1], failed, opt);
+        for (int k = 0; k < refine::NSTATE; ++k) o[k] = dst[k];
+        alphas3[3 * i] = s.xt[0] - 0.5 * del_alpha; alphas3[3 * i + 1] = s.xt[0]; alphas3[3 * i + 2] = s.xt[0] + 0.5 * del_alpha;
+        theta0[i] = s.xt[1];
+        active = (int)s.status != refine::ST_DONE;
+    }
+    const unsigned m = __ballot_sync(FULL, active);
+    if (nactive && (threadIdx.x & 31) == 0 && m) atomicAdd(nactive, __popc(m));
+}
+int launch_refine_init(double* state, int n, const double* a0, const double* t0, double alo, double ahi, double tlo, double thi,
+                       double del_alpha, double* alphas3, double* theta0, cudaStream_t st) {
+    if (n == 0) return IBS_OK;
+    refine_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(state, n, a0, t0, alo, ahi, tlo, thi, del_alpha, alphas3, theta0);
+    IBS_CUDA_CHECK(cudaGetLastError());
+    return IBS_OK;
+}
+int launch_refine_step(double* state, int n, const double* val, const double* grad, const int* info, double ftol, double gtol,
+                       int maxiter, double del_alpha, double* alphas3, double* theta0, int* nactive, cudaStream_t st) {
+    if (n == 0) return IBS_OK;
+    if (nactive) IBS_CUDA_CHECK(cudaMemsetAsync(nactive, 0, sizeof(int), st));
+    refine::Options o; o.ftol = ftol; o.gtol = gtol; o.maxiter = maxiter;
+    refine_step_kernel<<<(n + 127) / 128, 128, 0, st>>>(state, n, val, grad, info, o, del_alpha, alphas3, theta0, nactive);
     IBS_CUDA_CHECK(cudaGetLastError());
     return IBS_OK;
 }

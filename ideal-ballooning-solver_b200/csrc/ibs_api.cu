@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "ibs_common.cuh"
+#include "ibs_refine_core.cuh"
 
 namespace ibs {
 
@@ -28,6 +29,10 @@ int launch_centre_lines(int* line, int n, cudaStream_t st);
 int launch_argmax(const double* gamma, int ns, int ngrid, double* val, int* idx, double* sigma0, cudaStream_t st);
 int launch_argmax_packed(const double* gamma, int ns, int ngrid, double* best, double* sigma0, cudaStream_t st);
 bool scan_solver_eligible(const SolveParams& p);
+int launch_refine_init(double* state, int n, const double* a0, const double* t0, double alo, double ahi, double tlo, double thi,
+                       double del_alpha, double* alphas3, double* theta0, cudaStream_t st);
+int launch_refine_step(double* state, int n, const double* val, const double* grad, const int* info, double ftol, double gtol,
+                       int maxiter, double del_alpha, double* alphas3, double* theta0, int* nactive, cudaStream_t st);
 int launch_gather_best(const double* X, const int* idx, int ns, int ngrid, int N, double* out, cudaStream_t st);
 int launch_best_setup(const double* best, const double* theta0, int ns, int ngrid, int nth0, double* val_out, int* idx_out,
                       int* line_out, double* th0_out, cudaStream_t st);
@@ -229,6 +234,26 @@ int ibs_scan_solve_argmax(const double* base, const double* dPdrho, const double
     if (rc == IBS_OK && !fused)
         rc = launch_argmax_packed(lam_out, nline / lines_per_surface, lines_per_surface * nth0, best_out, sigma0_out, st);
     return rc;
+}
+
+int ibs_refine_state_doubles(void) { return ibs::refine::NSTATE; }
+
+int ibs_refine_init(double* state, int n, const double* alpha0, const double* theta0_0, double alpha_lo, double alpha_hi,
+                    double theta0_lo, double theta0_hi, double del_alpha, double* alphas3_out, double* theta0_out, void* stream) {
+    IBS_REQUIRE(n >= 0 && alpha_lo <= alpha_hi && theta0_lo <= theta0_hi, "bad sizes / bounds");
+    if (n == 0) return IBS_OK;
+    IBS_REQUIRE(state && alpha0 && theta0_0 && alphas3_out && theta0_out, "null pointer");
+    return launch_refine_init(state, n, alpha0, theta0_0, alpha_lo, alpha_hi, theta0_lo, theta0_hi, del_alpha, alphas3_out, theta0_out,
+                              (cudaStream_t)stream);
+}
+
+int ibs_refine_step(double* state, int n, const double* val, const double* grad, const int* info, double ftol, double gtol,
+                    int maxiter, double del_alpha, double* alphas3_out, double* theta0_out, int* nactive_out, void* stream) {
+    IBS_REQUIRE(n >= 0 && maxiter >= 1, "bad sizes");
+    if (n == 0) return IBS_OK;
+    IBS_REQUIRE(state && val && grad && alphas3_out && theta0_out, "null pointer");
+    return launch_refine_step(state, n, val, grad, info, ftol, gtol, maxiter, del_alpha, alphas3_out, theta0_out, nactive_out,
+                              (cudaStream_t)stream);
 }
 
 int ibs_count_above_batch(const double* g, const double* c, const double* f, int nsolve, int N, double h,

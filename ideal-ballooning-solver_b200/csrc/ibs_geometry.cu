@@ -26,7 +26,18 @@
 
 namespace ibs {
 
-constexpr int GEO_THREADS = 128;
+constexpr int GEO_THREADS = 128;          // axisymmetric tables: 128-point tiles
+// 3-D tables: ONE CTA of 512 threads per SM (one staged copy of the surface's tables serves 16 warps; 128 registers per
+// thread) and the n-summed Newton coefficients A_m, B_m of every point in shared memory instead of thread-local arrays
+#ifndef IBS_GEO_THREADS_3D
+#define IBS_GEO_THREADS_3D 512
+#endif
+#ifndef IBS_GEO_SMEM_NEWTON
+#define IBS_GEO_SMEM_NEWTON 1
+#endif
+constexpr int GEO_THREADS_3D = IBS_GEO_THREADS_3D;
+constexpr int GEO_SMEM_NEWTON_MAX_M = 16;  // A_m, B_m live in shared memory when mpol + 1 <= this (2 * 16 * 512 * 8 B = 128 KB), else in local memory
+template <int NT1> struct GeoThreads { static constexpr int value = (NT1 > 0) ? GEO_THREADS_3D : GEO_THREADS; };
 constexpr int ROW_MN = 10;    // r, n r, r_s, z, n z, z_s, l, n l, l_s, (pad)
 constexpr int ROW_NYQ = 8;    // g, b, n b, b_s, bsupv, bsubs, bsubu, bsubv
 // 3-D equilibria use a paired layout [m][|n|][row][E, O] (E = v(+n) + v(-n), O = v(+n) - v(-n)): with
@@ -99,9 +110,10 @@ template <int SGN> __device__ __forceinline__ void angle(double cm, double sm, d
 }
 
 template <int NT1, int NT2>
-__global__ void __launch_bounds__(GEO_THREADS)
+__global__ void __launch_bounds__(GeoThreads<NT1>::value)
 geometry_kernel(const GeoParams p) {
     constexpr int W1 = 2 * NT1 + 1, W2 = 2 * NT2 + 1, NT = (NT1 > NT2 ? NT1 : NT2);
+    constexpr int GEO_THREADS = GeoThreads<NT1>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     double* s_mn = reinterpret_cast<double*>(smem_raw + 16);
@@ -159,7 +171,14 @@ geometry_kernel(const GeoParams p) {
                 }
             }
             // ---- Newton for theta_vmec:  th + sum_m [ sin(m th) A_m - cos(m th) B_m ] = theta_p
-            double Am[NT1 > 0 ? MAX_M_NEWTON : 1], Bm[NT1 > 0 ? MAX_M_NEWTON : 1];
+            // A_m, B_m: per-thread columns of a shared-memory array [2 m + {0, 1}][thread] (conflict-free), or thread-local
+            // arrays when mpol is too large for that
+            double AmBm_local[NT1 > 0 ? 2 * MAX_M_NEWTON : 2];
+            const bool newton_smem = IBS_GEO_SMEM_NEWTON && NT1 > 0 && p.M1 <= GEO_SMEM_NEWTON_MAX_M;
+            double* const ab = newton_smem ? (s_nyq + n_nyq + tid) : AmBm_local;
+            const int abs_ = newton_smem ? GEO_THREADS : 1;
+#define Am(m) ab[(2 * (m)) * abs_]
+#define Bm(m) ab[(2 * (m) + 1) * abs_]
             if (NT1 > 0) {
                 for (int m = 0; m < p.M1; ++m) {
                     const double* row = s_mn + (size_t)m * (NT1 + 1) * ROWP_MN + 12;      // (E, O) of the l row
@@ -170,7 +189,7 @@ geometry_kernel(const GeoParams p) {
                         a = fma(eo.x, cn[k], a);
                         b = fma(eo.y, sn[k], b);
                     }
-                    Am[m] = a; Bm[m] = b;
+                    Am(m) = a; Bm(m) = b;
                 }
             }
             double th = theta_p;
@@ -194,8 +213,8 @@ geometry_kernel(const GeoParams p) {
                     }
                 } else {
                     for (int m = 0; m < p.M1; ++m) {
-                        const double a = Am[m];
-                        const double b = Bm[m];
+                        const double a = Am(m);
+                        const double b = Bm(m);
                         fsum = fma(sm, a, fsum); fsum = fma(-cm, b, fsum);
                         const double dm = (double)m;
                         dsum = fma(dm * cm, a, dsum); dsum = fma(dm * sm, b, dsum);
@@ -217,6 +236,8 @@ geometry_kernel(const GeoParams p) {
                 }
                 dprev = ad;
             }
+#undef Am
+#undef Bm
             // ---- mode sums (utils.py:420-468)
             double s1, c1;
             sincos(th, &s1, &c1);
@@ -474,13 +495,15 @@ __global__ void dpdrho_kernel(const double* __restrict__ base, int nlines, int n
 template <int NT1, int NT2>
 static int launch_geometry(const GeoParams& p, cudaStream_t st) {
     auto kern = geometry_kernel<NT1, NT2>;
+    constexpr int GEO_THREADS = GeoThreads<NT1>::value;
     const size_t e_mn = (NT1 > 0) ? (size_t)(NT1 + 1) * ROWP_MN : (size_t)ROW_MN, e_nyq = (NT2 > 0) ? (size_t)(NT2 + 1) * ROWP_NYQ : (size_t)ROW_NYQ;
-    const size_t smem = 16 + ((size_t)p.M1 * e_mn + (size_t)p.M2 * e_nyq) * sizeof(double);
-    if (smem > 200 * 1024) { set_error("Fourier tables of one surface do not fit in shared memory"); return IBS_ERR_UNSUPPORTED; }
+    const bool newton_smem = IBS_GEO_SMEM_NEWTON && NT1 > 0 && p.M1 <= GEO_SMEM_NEWTON_MAX_M;
+    const size_t smem = 16 + ((size_t)p.M1 * e_mn + (size_t)p.M2 * e_nyq + (newton_smem ? (size_t)2 * p.M1 * GEO_THREADS : 0)) * sizeof(double);
+    if (smem > 220 * 1024) { set_error("Fourier tables of one surface do not fit in shared memory"); return IBS_ERR_UNSUPPORTED; }
     static bool configured[IBS_MAX_DEVICES] = {false};     // per instantiation and per device (the attribute is per device)
     const int dslot = current_device_slot();
     if (!configured[dslot]) {
-        IBS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        IBS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         configured[dslot] = true;
     }
     int per_sm = 0;

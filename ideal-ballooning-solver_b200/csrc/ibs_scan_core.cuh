@@ -37,18 +37,33 @@
 namespace ibs {
 namespace scan {
 
+#ifndef IBS_SCAN_BLK
+#define IBS_SCAN_BLK 4
+#endif
+#ifndef IBS_SCAN_BLK_OUT
+#define IBS_SCAN_BLK_OUT IBS_SCAN_BLK
+#endif
+constexpr int SCAN_BLK = IBS_SCAN_BLK;           // steps per iteration of the iteration pass's loop (2 or 4)
+constexpr int SCAN_BLK_OUT = IBS_SCAN_BLK_OUT;   // ... of the output passes' loops
 constexpr int TR = 32;            // records per tile (one pipeline stage holds one forward and one backward tile)
 constexpr int REC = 6;            // doubles per record: G0 G1 G2 (g = G0 + th0 G1 + th0^2 G2), C0 C1 (2 h^2 c), R (2 h^2 f = g R)
 constexpr int MAXLEV = 4;         // coarse levels (strides 2, 4, 8, 16)
 constexpr int MIN_COARSE_N = 65;  // a level is used only if it has at least this many points
 constexpr int MAXIT_LEVEL = 64;   // evaluations per level before giving up
 constexpr int K_MARGIN = 8;       // matching row kept this far from both ends
-constexpr double LOWQ = 1.0e3;
+constexpr double LOWQ = 1.0e3;    // max|z| / |z_k| above which the matching row is moved (see solve_item)
 // (Tried and removed: letting the output pass stand in for the last fine-level evaluation.  It saves ~1 of ~6 fine-grid
 // passes per lane, but its vector is then taken at a shift that is only ~1e-11 converged and the Simpson Rayleigh
 // quotient -- which weighs the far end of the spectrum heavily -- moves by up to 6e-11 relative; and at warp level the
 // acceptance test has to hold for all 32 lanes, so there was no measurable speed-up.)
-constexpr int PEAK_SNAP = 16;      // a coarsest-level peak within Nl / PEAK_SNAP rows of the middle keeps the middle matching row    // max|z| / |z_k| above which the matching row is moved (see solve_item)
+#ifndef IBS_PEAK_SNAP
+#define IBS_PEAK_SNAP 8
+#endif
+// A coarsest-level peak within Nl / PEAK_SNAP rows of the middle keeps the middle matching row.  With unequal chains the rows
+// beyond the shorter one run on the one-step-at-a-time path (~7x the cost of a pipelined step), so the row is moved only
+// when it has to be: measured on the bench's D3D-like lines, 16 -> 8 takes the general steps from 15 % of all steps to
+// 1 per pass with the same number of passes (NCSX-like lines: 28 % -> 1 per pass, 24.0 -> 28.4 passes per solve).
+constexpr int PEAK_SNAP = IBS_PEAK_SNAP;
 
 constexpr int FLAG_NOT_CONVERGED = 1, FLAG_BAD_INPUT = 2, FLAG_SIGMA_NOT_MAX = 4;   // = IBS_FLAG_* of include/ibs_b200.h
 
@@ -273,12 +288,12 @@ IBS_PASS void eval_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SP
     int i_first = 2;
     if (nfs > 0) {
         // ---- fast region: steps 2 .. 32 nfs - 1, ONE software pipeline across the stage boundaries (records two steps
-        // ahead through running pointers, coefficients one step ahead).  Control flow is kept out of the hot code: the
-        // only branches are the back edges of counted loops over blocks of four steps (a taken branch costs a warp
-        // ~15 idle cycles, and with two warps per scheduler nothing hides them).  A trip of the stage loop covers the
-        // steps 32 m - 2 .. 32 m + 29, whose records all lie in stage m: wait / pointer reset at its top, rescaling
-        // after each half, release of the previous stage in the middle (its last records were consumed by the first
-        // block), sign histories of exactly 32 steps counted at the end.
+        // ahead through running pointers, coefficients one step ahead).  Control flow is kept out of the hot code: its
+        // only branch is the back edge of a counted loop over blocks of SCAN_BLK steps (a taken branch costs a warp
+        // ~15 idle cycles, and with two warps per scheduler nothing hides them; round 1's loop took three per two steps).
+        // The steps 32 m - 2 .. 32 m + 29 read records of stage m only: wait / pointer reset before them, rescaling
+        // every 16 steps, release of the previous stage after the first 16 (its last records were consumed by the first
+        // block), sign histories of exactly 32 steps counted after the second 16.
         const int gend = TR * nfs;
         Co cf[SPL], cb[SPL];
         unsigned mf[SPL], mb[SPL], ef[SPL], eb[SPL];
@@ -306,37 +321,40 @@ IBS_PASS void eval_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SP
                 mb[q] = (mb[q] << 1) | sign_bit(Xb[q]);
             }
         };
-        auto blocks4 = [&](int nblk) {                     // nblk blocks of four steps; loads the records of the steps g+2 .. g+5
-#pragma unroll 1
-            for (int b = 0; b < nblk; ++b) {
-                Rec nf = load_rec(pf), nb = load_rec(pb);
-                step1(rf, rb);
-                rf = load_rec(pf + REC); rb = load_rec(pb - REC);
-                step1(nf, nb);
-                nf = load_rec(pf + 2 * REC); nb = load_rec(pb - 2 * REC);
-                step1(rf, rb);
-                rf = load_rec(pf + 3 * REC); rb = load_rec(pb - 3 * REC);
-                step1(nf, nb);
-                pf += 4 * REC; pb -= 4 * REC;
-            }
-        };
         auto rescale_all = [&]() {
 #pragma unroll
             for (int q = 0; q < SPL; ++q) { rescale3(Xf[q], Wf[q], Sf[q]); rescale3(Xb[q], Wb[q], Sb[q]); }
         };
+        // One copy of the block loop (instruction cache: two warps share a scheduler's L0), run once per HALF stage:
+        // half hf covers the steps 16 hf - 2 .. 16 hf + 13 (hf = 0: 2 .. 13); the few tests per half are off the hot path.
 #pragma unroll 1
-        for (int m = 0; m < nfs; ++m) {
-            if (m > 0) { ctx.wait(m); pf = ctx.frec(0); pb = ctx.brec(0); }
-            blocks4(m > 0 ? 4 : 3);                        // steps 32 m - 2 (m = 0: 2) .. 32 m + 13
+        for (int hf = 0; hf < 2 * nfs; ++hf) {
+            if ((hf & 1) == 0 && hf > 0) { ctx.wait(hf >> 1); pf = ctx.frec(0); pb = ctx.brec(0); }
+            const int nblk = (hf > 0) ? 16 / SCAN_BLK : 12 / SCAN_BLK;
+#pragma unroll 1
+            for (int b = 0; b < nblk; ++b) {               // SCAN_BLK steps; loads the records of the steps g+2 .. g+SCAN_BLK+1
+                Rec nf = load_rec(pf), nb = load_rec(pb);
+                step1(rf, rb);
+                rf = load_rec(pf + REC); rb = load_rec(pb - REC);
+                step1(nf, nb);
+                if (SCAN_BLK == 4) {
+                    nf = load_rec(pf + 2 * REC); nb = load_rec(pb - 2 * REC);
+                    step1(rf, rb);
+                    rf = load_rec(pf + 3 * REC); rb = load_rec(pb - 3 * REC);
+                    step1(nf, nb);
+                }
+                pf += SCAN_BLK * REC; pb -= SCAN_BLK * REC;
+            }
             rescale_all();
-            if (m > 0) ctx.release(m - 1);
-            blocks4(4);                                    // steps 32 m + 14 .. 32 m + 29
-            rescale_all();
+            if (hf & 1) {
 #pragma unroll
-            for (int q = 0; q < SPL; ++q) {
-                nodes[q] += sign_changes32(mf[q], ef[q]) + sign_changes32(mb[q], eb[q]);
-                ef[q] = sign_bit(Xf[q]); eb[q] = sign_bit(Xb[q]);
-                mf[q] = 0; mb[q] = 0;
+                for (int q = 0; q < SPL; ++q) {
+                    nodes[q] += sign_changes32(mf[q], ef[q]) + sign_changes32(mb[q], eb[q]);
+                    ef[q] = sign_bit(Xf[q]); eb[q] = sign_bit(Xb[q]);
+                    mf[q] = 0; mb[q] = 0;
+                }
+            } else if (hf > 0) {
+                ctx.release((hf >> 1) - 1);                // its last records were consumed by the first block of this half
             }
         }
         // steps gend - 2 (its successor's coefficients from the record already loaded) and gend - 1 (chains only)
@@ -670,7 +688,10 @@ IBS_PASS void out_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL
         Rec rf = load_rec(pf), rb = load_rec(pb);         // records of step 7
         pf += REC; pb -= REC;                              // -> records of step 8
         int g = 6;
-        auto blocks4 = [&](int nblk) {
+#pragma unroll 1
+        for (int hf = 0; hf < 2 * nfs; ++hf) {             // half hf: steps 16 hf - 2 .. 16 hf + 13 (hf = 0: 6 .. 13); one copy of the block loop
+            if ((hf & 1) == 0 && hf > 0) { ctx.wait(hf >> 1); pf = ctx.frec(0); pb = ctx.brec(0); }
+            const int nblk = (hf > 0) ? 16 / SCAN_BLK_OUT : 8 / SCAN_BLK_OUT;
 #pragma unroll 1
             for (int b = 0; b < nblk; ++b) {
                 Rec nf = load_rec(pf), nb = load_rec(pb);
@@ -679,24 +700,19 @@ IBS_PASS void out_pass(Ctx& ctx, int lev, int Nl, int k, const double (&th0)[SPL
                 rf = load_rec(pf + REC); rb = load_rec(pb - REC);
 #pragma unroll
                 for (int q = 0; q < SPL; ++q) out_joint<1, WRITE>(nf, nb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], g + 1, Nl, Xw[q]);
-                nf = load_rec(pf + 2 * REC); nb = load_rec(pb - 2 * REC);
+                if (SCAN_BLK_OUT == 4) {
+                    nf = load_rec(pf + 2 * REC); nb = load_rec(pb - 2 * REC);
 #pragma unroll
-                for (int q = 0; q < SPL; ++q) out_joint<0, WRITE>(rf, rb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], g + 2, Nl, Xw[q]);
-                rf = load_rec(pf + 3 * REC); rb = load_rec(pb - 3 * REC);
+                    for (int q = 0; q < SPL; ++q) out_joint<0, WRITE>(rf, rb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], g + 2, Nl, Xw[q]);
+                    rf = load_rec(pf + 3 * REC); rb = load_rec(pb - 3 * REC);
 #pragma unroll
-                for (int q = 0; q < SPL; ++q) out_joint<1, WRITE>(nf, nb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], g + 3, Nl, Xw[q]);
-                pf += 4 * REC; pb -= 4 * REC;
-                g += 4;
+                    for (int q = 0; q < SPL; ++q) out_joint<1, WRITE>(nf, nb, th0[q], lam[q], cf[q], cb[q], F_[q], B_[q], g + 3, Nl, Xw[q]);
+                }
+                pf += SCAN_BLK_OUT * REC; pb -= SCAN_BLK_OUT * REC;
+                g += SCAN_BLK_OUT;
             }
-        };
-#pragma unroll 1
-        for (int m = 0; m < nfs; ++m) {
-            if (m > 0) { ctx.wait(m); pf = ctx.frec(0); pb = ctx.brec(0); }
-            blocks4(m > 0 ? 4 : 2);                        // steps 32 m - 2 (m = 0: 6) .. 32 m + 13
             rescale_all(true, true);
-            if (m > 0) ctx.release(m - 1);
-            blocks4(4);                                    // steps 32 m + 14 .. 32 m + 29
-            rescale_all(true, true);
+            if ((hf & 1) == 0 && hf > 0) ctx.release((hf >> 1) - 1);
         }
 #pragma unroll
         for (int q = 0; q < SPL; ++q) {

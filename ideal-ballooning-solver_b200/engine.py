@@ -300,6 +300,45 @@ def obj_w_grad_batch(base3, dPdrho3, theta0, h: float, del_alpha: float = 0.004,
     return val, grad, X, dX, info
 
 
+class RefineState:
+    """Device-resident state of the batched refinement (``ibs_refine_init`` / ``ibs_refine_step``): ``n`` independent
+    2-D box-constrained problems advanced in lock step.  ``alphas3 (n, 3)`` and ``theta0 (n,)`` always hold the NEXT trial
+    points in the layout ``geometry_batch`` / ``obj_w_grad_batch`` take."""
+
+    def __init__(self, alpha0, theta0, bounds=((0.0, float(np.pi)), (0.0, 0.5 * float(np.pi))), del_alpha: float = 0.004):
+        _lib.require_cuda()
+        lib = _lib.load()
+        dev = alpha0.device
+        self.n = alpha0.numel()
+        self.del_alpha = float(del_alpha)
+        self.nstate = lib.ibs_refine_state_doubles()
+        self.state = torch.zeros((self.n, self.nstate), dtype=torch.float64, device=dev)
+        self.alphas3 = torch.empty((self.n, 3), dtype=torch.float64, device=dev)
+        self.theta0 = torch.empty((self.n,), dtype=torch.float64, device=dev)
+        self.nactive = torch.zeros((1,), dtype=torch.int32, device=dev)
+        a0, t0 = _f64(alpha0, dev, "alpha0").reshape(-1), _f64(theta0, dev, "theta0").reshape(-1)
+        with torch.cuda.device(dev):
+            rc = lib.ibs_refine_init(_ptr(self.state), self.n, _ptr(a0), _ptr(t0), float(bounds[0][0]), float(bounds[0][1]),
+                                     float(bounds[1][0]), float(bounds[1][1]), self.del_alpha, _ptr(self.alphas3), _ptr(self.theta0),
+                                     _stream())
+        _lib.check(rc, "ibs_refine_init")
+
+    def step(self, val, grad, info, ftol: float, gtol: float, maxiter: int):
+        lib = _lib.load()
+        with torch.cuda.device(self.state.device):
+            rc = lib.ibs_refine_step(_ptr(self.state), self.n, _ptr(val), _ptr(grad), _ptr(info), float(ftol), float(gtol), int(maxiter),
+                                     self.del_alpha, _ptr(self.alphas3), _ptr(self.theta0), _ptr(self.nactive), _stream())
+        _lib.check(rc, "ibs_refine_step")
+
+    # views into the state (see include/ibs_b200.h)
+    x = property(lambda self: self.state[:, 0:2])
+    fun = property(lambda self: self.state[:, 2])
+    status = property(lambda self: self.state[:, 18])
+    why = property(lambda self: self.state[:, 19])
+    nit = property(lambda self: self.state[:, 20])
+    nfev = property(lambda self: self.state[:, 21])
+
+
 def scan_argmax(gamma):
     """Per-surface arg-max over the flattened ``(alpha, theta0)`` grid with the reference's guards
     (``ball_scan.py:279-295``).  ``gamma`` is ``(ns, ...)``; returns ``(val, flat_idx, sigma0)``;

@@ -258,10 +258,47 @@ class RefineResult:
 
 
 def refine_maxima(tables: engine.DeviceTables, alpha_guess, theta0_guess, theta, maxiter: int = 30, ftol: float = 5.0e-11,
-                  gtol: float = 2.0e-08) -> RefineResult:
-    """``scipy.optimize.minimize(obj_w_grad, x0=(alpha_guess, theta0_guess), jac=True, bounds=((0, pi), (0, pi/2)),
-    options={ftol, gtol, maxiter})`` for every surface (``ball_scan.py:305-314``), the objective evaluated on the
-    GPU for all surfaces at once."""
+                  gtol: float = 2.0e-08, method: str = "device", max_rounds: int = 200, sync_every: int = 4) -> RefineResult:
+    """Refinement of every surface's coarse maximum (``ball_scan.py:305-314``: ``scipy.optimize.minimize(obj_w_grad,
+    x0=(alpha_guess, theta0_guess), jac=True, bounds=((0, pi), (0, pi/2)), options={ftol, gtol, maxiter})``).
+
+    ``method="device"`` (default): the batched projected quasi-Newton method of ``csrc/ibs_refine_core.cuh`` -- all surfaces in
+    lock step, the optimiser state resident on the GPU; one round = K1 (three field lines per surface) + K2/K3 + K4
+    (``ibs_obj_w_grad_batch``) + ``ibs_refine_step``, no host arithmetic; the host only polls the count of running problems
+    every ``sync_every`` rounds.  ``method="scipy"``: the reference's own optimiser, one Python thread per surface around the
+    same batched evaluations (kept as the cross-check)."""
+    if method == "scipy":
+        return _refine_maxima_scipy(tables, alpha_guess, theta0_guess, theta, maxiter, ftol, gtol)
+    if method != "device":
+        raise ValueError("method must be 'device' or 'scipy'")
+    dev = tables.tab_mn.device
+    ns = tables.ns
+    theta_np = theta.cpu().numpy() if isinstance(theta, torch.Tensor) else np.asarray(theta, dtype=np.float64)
+    theta_d = torch.from_numpy(theta_np).to(dev)
+    h = engine.grid_spacing(theta_np)
+    as_dev = lambda a: (a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, dtype=np.float64))).to(dev).reshape(ns)
+    st = engine.RefineState(as_dev(alpha_guess), as_dev(theta0_guess), del_alpha=DEL_ALPHA)
+    rounds = 0
+    while rounds < max_rounds:
+        for _ in range(sync_every):
+            geo = engine.geometry_batch(tables, st.alphas3, theta_d)                      # utils.py:1641-1646: alpha -+ del/2
+            val, grad, _, _, info = engine.obj_w_grad_batch(geo.base, geo.dPdrho, st.theta0, h, del_alpha=DEL_ALPHA)
+            st.step(val, grad, info, ftol, gtol, maxiter)
+            rounds += 1
+        if int(st.nactive.item()) == 0:
+            break
+    S = st.state.cpu().numpy()
+    why = S[:, 19].astype(int)
+    if np.any(why == 5):
+        raise RuntimeError("obj_w_grad: eigen-solve failed at the starting point of surface(s) %s" % np.flatnonzero(why == 5).tolist())
+    return RefineResult(alpha=S[:, 0].copy(), theta0=S[:, 1].copy(), fun=S[:, 2].copy(), nit=S[:, 20].astype(int),
+                        nfev=S[:, 21].astype(int), success=np.isin(why, (1, 2, 3, 4)), nbatches=rounds)
+
+
+def _refine_maxima_scipy(tables: engine.DeviceTables, alpha_guess, theta0_guess, theta, maxiter: int = 30, ftol: float = 5.0e-11,
+                         gtol: float = 2.0e-08) -> RefineResult:
+    """The reference's optimiser itself (scipy L-BFGS-B with its options), one Python thread per surface, the objective
+    evaluated on the GPU for all surfaces at once (cross-check of the device method)."""
     import threading
     from scipy.optimize import minimize
     ns = tables.ns
@@ -309,7 +346,7 @@ class BallScanResult:
 
 def ball_scan(st: SurfaceTables, theta=None, mpol: Optional[int] = None, ntor: Optional[int] = None,
               nalpha_guess: int = NALPHA_GUESS, ntheta0_guess: int = NTHETA0_GUESS, refine: bool = True,
-              device=None) -> BallScanResult:
+              device=None, refine_method: str = "device") -> BallScanResult:
     """The numerical section of ``ball_scan.py:196-339`` for all surfaces of ``st`` at once:
     coarse 24 x 15 (alpha, theta0) grid (``:223-274``) -> guarded arg-max (``:279-295``) -> L-BFGS-B refinement
     from the coarse maximum with the adjoint gradient (``:305-314``) -> eigenpair at the optimum (``:322-339``)."""
@@ -324,7 +361,7 @@ def ball_scan(st: SurfaceTables, theta=None, mpol: Optional[int] = None, ntor: O
     a_star, t_star = res.alpha_guess.cpu().numpy(), res.theta0_guess.cpu().numpy()
     ref = None
     if refine:
-        ref = refine_maxima(dt, a_star, t_star, theta)
+        ref = refine_maxima(dt, a_star, t_star, theta, method=refine_method)
         a_star, t_star = ref.alpha, ref.theta0
     # ball_scan.py:322-339: geometry and eigenpair at the optimum
     geo = engine.geometry_batch(dt, torch.from_numpy(a_star[:, None].copy()).to(device), theta)

@@ -168,6 +168,26 @@ int ibs_scan_solve_argmax(const double* base, const double* dPdrho, const double
                           double* lam_out, double* X_out, double* dX_out, int* info_out,
                           double* best_out, double* sigma0_out, void* stream);
 
+/* ---- refinement of the coarse maxima (ball_scan.py:305-314) ---------------------------------------
+ * Batched, device-resident replacement of the per-surface scipy L-BFGS-B call
+ *   minimize(obj_w_grad, x0=(alpha_guess, theta0_guess), jac=True, bounds=((0, pi), (0, pi/2)),
+ *            options={"ftol": 5e-11, "gtol": 2e-8, "maxiter": 30}):
+ * a projected quasi-Newton method that advances n problems in lock step.  One round = ibs_geometry_batch on
+ * alphas3 (three field lines per problem, alpha_per_surface = 1) -> ibs_obj_w_grad_batch at theta0 -> ibs_refine_step,
+ * which consumes (val, grad, info), updates every problem and writes the NEXT trial points into alphas3 / theta0.
+ *   state [n][ibs_refine_state_doubles()]: opaque per-problem state; doubles 0..1 = current best (alpha, theta0),
+ *          2 = F = -lambda there, 18 = status (2 = finished), 19 = reason (1 pgtol, 2 ftol, 3 maxiter, 4 step, 5 failed),
+ *          20 = iterations, 21 = function evaluations;
+ *   alphas3_out [n][3] = (a - del/2, a, a + del/2) (utils.py:1641-1646); theta0_out [n];
+ *   nactive_out (device int, or NULL): number of problems still running after this step.                        */
+int ibs_refine_state_doubles(void);
+int ibs_refine_init(double* state, int n, const double* alpha0, const double* theta0_0, double alpha_lo, double alpha_hi,
+                    double theta0_lo, double theta0_hi, double del_alpha, double* alphas3_out, double* theta0_out,
+                    void* stream);
+int ibs_refine_step(double* state, int n, const double* val, const double* grad, const int* info, double ftol,
+                    double gtol, int maxiter, double del_alpha, double* alphas3_out, double* theta0_out,
+                    int* nactive_out, void* stream);
+
 /* ---- marginal-stability classifier ---------------------------------------------------------------
  * Sturm/Newcomb node count of the discretised ballooning operator at a given lam (the s-alpha test
  * of the reference shoots at lam = 0, tests/shifted-circle-s-alpha/bishop_ball_s-alpha.py:90-115):

@@ -31,17 +31,22 @@ def test_ball_scan_matches_oracle_driver(cuda_lib, golden):
     st = tables_from_fixture(D)                                   # 3 surfaces
     theta = np.linspace(-3 * np.pi, 3 * np.pi, 193)
     na, nt = 5, 4
-    res = scan.ball_scan(st, theta=theta, nalpha_guess=na, ntheta0_guess=nt)
     alpha_scan, theta0_scan = np.linspace(0, np.pi, na), np.linspace(0, 0.5 * np.pi, nt)
-    assert res.refine is not None and res.refine.nbatches <= int(res.refine.nfev.max()) + 2     # evaluations were batched
-    for js in range(st.ns):
-        gam, obj, lam = _oracle_ball_scan_surface(st.select([js]), theta, alpha_scan, theta0_scan)
-        np.testing.assert_allclose(res.gamma_coarse[js], gam, rtol=1e-9, atol=1e-13)
-        # same optimiser, same options, objective equal to ~1e-10: the optimum agrees closely
-        np.testing.assert_allclose(res.gamma[js], lam, rtol=1e-6, atol=1e-10)
-        np.testing.assert_allclose([res.alpha[js], res.theta0[js]], obj.x, atol=2e-4)
-        assert res.gamma[js] >= gam.max() - 1e-12                  # the refinement never loses the coarse maximum
-        assert 0.0 <= res.alpha[js] <= np.pi and 0.0 <= res.theta0[js] <= 0.5 * np.pi
+    oracle = [_oracle_ball_scan_surface(st.select([js]), theta, alpha_scan, theta0_scan) for js in range(st.ns)]
+    runs = {m: scan.ball_scan(st, theta=theta, nalpha_guess=na, ntheta0_guess=nt, refine_method=m) for m in ("device", "scipy")}
+    for method, res in runs.items():
+        assert res.refine is not None and res.refine.nbatches <= int(res.refine.nfev.max()) + 4     # evaluations were batched
+        for js in range(st.ns):
+            gam, obj, lam = oracle[js]
+            np.testing.assert_allclose(res.gamma_coarse[js], gam, rtol=1e-9, atol=1e-13)
+            # objective equal to ~1e-10 and the reference's stopping tolerances: the optimum agrees closely (scipy path: the same
+            # optimiser as the oracle driver; device path: another quasi-Newton method under the same ftol / gtol / bounds)
+            np.testing.assert_allclose(res.gamma[js], lam, rtol=1e-6, atol=1e-10)
+            np.testing.assert_allclose([res.alpha[js], res.theta0[js]], obj.x, atol=2e-4 if method == "scipy" else 3e-3)
+            assert res.gamma[js] >= gam.max() - 1e-12                  # the refinement never loses the coarse maximum
+            assert 0.0 <= res.alpha[js] <= np.pi and 0.0 <= res.theta0[js] <= 0.5 * np.pi
+    # the device-resident optimiser reaches at least the scipy path's optimum (to the reference's own ftol = 5e-11 on F)
+    assert np.all(runs["device"].gamma >= runs["scipy"].gamma - 1e-10)
 
 
 def test_refine_batches_all_surfaces(cuda_lib, golden):
@@ -51,9 +56,14 @@ def test_refine_batches_all_surfaces(cuda_lib, golden):
     theta = np.linspace(-4 * np.pi, 4 * np.pi, 513)
     res = scan.ball_scan(st, theta=theta, nalpha_guess=6, ntheta0_guess=5)
     r = res.refine
-    assert r.nbatches <= int(r.nfev.max()) + 2 and int(r.nfev.sum()) > 3 * r.nbatches
+    assert r.nbatches <= int(r.nfev.max()) + 4 and int(r.nfev.sum()) > 3 * r.nbatches
+    assert np.all(r.success)
     assert np.all(res.gamma >= res.gamma_coarse.reshape(64, -1).max(axis=1) - 1e-12)
     assert np.all(np.isfinite(res.gamma)) and res.X.shape == (64, 513)
+    # against the reference's optimiser (scipy L-BFGS-B, same options) on the same batched evaluations
+    res_s = scan.ball_scan(st, theta=theta, nalpha_guess=6, ntheta0_guess=5, refine_method="scipy")
+    assert np.all(res.gamma >= res_s.gamma - 1e-10 - 1e-6 * np.abs(res_s.gamma))
+    assert np.median(np.abs(res.gamma - res_s.gamma) / np.abs(res_s.gamma)) < 1e-6
 
 
 def test_hellmann_feynman_gamma_predicts_perturbed_growth_rates(cuda_lib):
