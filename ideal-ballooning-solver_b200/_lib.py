@@ -24,6 +24,9 @@ SIGNATURES = {
     "ibs_fp64_probe": (c_int, [c_int, _D, ctypes.c_longlong, POINTER(c_double), c_void_p]),
     "ibs_geometry_batch": (c_int, [_D, _D, _D, _D, _D, _D, _D, c_int, c_int, c_int, c_double, c_double,
                                    _D, c_int, c_int, _D, c_int, c_double, _D, _D, _D, _I, c_void_p]),
+    "ibs_geometry_full_nfields": (c_int, []),
+    "ibs_geometry_full": (c_int, [_D, _D, _D, _D, _D, _D, _D, _D, c_int, c_int, c_int, c_double, c_double, _D, c_int, _D, c_int,
+                                  c_int, c_double, c_int, c_double, _D, _I, c_void_p]),
     "ibs_solve_gcf_batch": (c_int, [_D, _D, _D, c_int, c_int, c_double, _D, _D, c_int, _D, _D, _D, _D, _I, c_void_p]),
     "ibs_solve_base_batch": (c_int, [_D, _D, _D, _I, c_int, c_int, c_int, c_double, _D, _D, c_int,
                                      _D, _D, _D, _D, _D, _D, _D, _I, c_void_p]),

@@ -180,7 +180,7 @@ argmax_kernel(const double* __restrict__ gamma, int ngrid, double* __restrict__ 
         double v; int k; double sg;
         if (anynan) { v = __longlong_as_double(0x7ff8000000000000LL); k = -2; sg = 0.05; }     // np.max propagates NaN; the reference would raise
         else if (bv == 0.0) { v = bv; k = -1; sg = 0.05; }                                      // ball_scan.py:279-282
-        else { v = bv; k = bi; sg = 1.3 * fabs(bv) + 0.05; }                                    // ball_scan.py:283-295 (first index in row-major order)
+        else { v = bv; k = bi; sg = __dadd_rn(__dmul_rn(1.3, fabs(bv)), 0.05); }     // (two roundings, like numpy: no FMA contraction)                                    // ball_scan.py:283-295 (first index in row-major order)
         if (val) val[s] = v;
         if (idx) idx[s] = k;
         if (sigma0) sigma0[s] = sg;

@@ -29,6 +29,12 @@ int launch_centre_lines(int* line, int n, cudaStream_t st);
 int launch_argmax(const double* gamma, int ns, int ngrid, double* val, int* idx, double* sigma0, cudaStream_t st);
 int launch_argmax_packed(const double* gamma, int ns, int ngrid, double* best, double* sigma0, cudaStream_t st);
 bool scan_solver_eligible(const SolveParams& p);
+int geometry_full_nfields();
+int geometry_full_dispatch(const double* tab_mn, const double* tab_nyq, const double* bsupumnc, const double* scal,
+                           const double* xm, const double* xn, const double* xm_nyq, const double* xn_nyq,
+                           int ns, int mnmax, int mnmax_nyq, double phiedge, double aminor_p, const double* alpha, int nalpha,
+                           const double* grid, int nl, int mode, double theta_shift, int zero_xn_nyq, double phi_center,
+                           double* out, int* info, cudaStream_t st);
 int launch_refine_init(double* state, int n, const double* a0, const double* t0, double alo, double ahi, double tlo, double thi,
                        double del_alpha, double* alphas3, double* theta0, cudaStream_t st);
 int launch_refine_step(double* state, int n, const double* val, const double* grad, const int* info, double ftol, double gtol,
@@ -180,6 +186,21 @@ int ibs_geometry_batch(const double* tab_mn, const double* tab_nyq, const double
     return geometry_dispatch(tab_mn, tab_nyq, scal, xm, xn, xm_nyq, xn_nyq, ns, mnmax, mnmax_nyq, phiedge, aminor_p, alpha,
                              nalpha, alpha_per_surface, theta, nl, phi_center, base_out, dPdrho_out, theta_vmec_out,
                              info_out, (cudaStream_t)stream);
+}
+
+int ibs_geometry_full_nfields(void) { return geometry_full_nfields(); }
+
+int ibs_geometry_full(const double* tab_mn, const double* tab_nyq, const double* bsupumnc, const double* scal,
+                      const double* xm, const double* xn, const double* xm_nyq, const double* xn_nyq,
+                      int ns, int mnmax, int mnmax_nyq, double phiedge, double aminor_p,
+                      const double* alpha, int nalpha, const double* grid, int nl, int mode, double theta_shift,
+                      int zero_xn_nyq, double phi_center, double* out, int* info_out, void* stream) {
+    IBS_REQUIRE(tab_mn && tab_nyq && bsupumnc && scal && xm && xn && xm_nyq && xn_nyq && alpha && grid && out, "null pointer");
+    IBS_REQUIRE(ns >= 0 && nalpha >= 0 && nl >= 1 && mnmax >= 1 && mnmax_nyq >= 1 && mode >= 0 && mode <= 2, "bad sizes / mode");
+    IBS_REQUIRE(aminor_p > 0.0 && phiedge != 0.0, "Aminor_p must be > 0 and phiedge != 0");
+    return geometry_full_dispatch(tab_mn, tab_nyq, bsupumnc, scal, xm, xn, xm_nyq, xn_nyq, ns, mnmax, mnmax_nyq, phiedge, aminor_p,
+                                  alpha, nalpha, grid, nl, mode, theta_shift, zero_xn_nyq, phi_center, out, info_out,
+                                  (cudaStream_t)stream);
 }
 
 int ibs_solve_gcf_batch(const double* g, const double* c, const double* f, int nsolve, int N, double h,

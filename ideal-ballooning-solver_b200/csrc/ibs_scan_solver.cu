@@ -255,7 +255,7 @@ scan_solve_kernel(const ScanParams p) {
                     double val, idx, sg;
                     if (anynan) { val = __longlong_as_double(0x7ff8000000000000LL); idx = -2.0; sg = 0.05; }     // np.max propagates NaN
                     else if (bv == 0.0) { val = bv; idx = -1.0; sg = 0.05; }                                      // ball_scan.py:279-282
-                    else { val = bv; idx = (double)bi; sg = 1.3 * fabs(bv) + 0.05; }                              // ball_scan.py:283-295
+                    else { val = bv; idx = (double)bi; sg = __dadd_rn(__dmul_rn(1.3, fabs(bv)), 0.05); }     // (two roundings, like numpy: no FMA contraction)                              // ball_scan.py:283-295
                     p.best_out[2 * surf] = val; p.best_out[2 * surf + 1] = idx;
                     if (p.sigma0_out) p.sigma0_out[surf] = sg;
                 }

@@ -86,6 +86,23 @@ int ibs_geometry_batch(const double* tab_mn, const double* tab_nyq, const double
                        double* base_out, double* dPdrho_out, double* theta_vmec_out, int* info_out,
                        void* stream);
 
+/* Full-output geometry: every per-point array of the Struct returned by vmec_fieldlines (utils.py:723-864) and by
+ * vmec_fieldlines_axisym (utils.py:872-1542) -- the ~70 arrays gyrokinetic-geometry consumers read beyond the eight of
+ * the ballooning path.  Not a hot kernel (direct mode sums; any mode list).  ALL pointers are device pointers.
+ *   tab_mn [ns][6][mnmax], tab_nyq [ns][7][mnmax_nyq] as above, bsupumnc [ns][mnmax_nyq] (the one table K1 does not
+ *   need), scal [ns][8]; xm, xn [mnmax], xm_nyq, xn_nyq [mnmax_nyq]; alpha [nalpha]; grid [nl];
+ *   mode 0: grid = theta_pest (vmec_fieldlines(theta1d=...)); mode 1: grid = phi (vmec_fieldlines(phi1d=...), utils.py:364-369);
+ *   mode 2: grid = theta_vmec, no root solve, the mode sums use theta_vmec + theta_shift and phi = 0, then
+ *           theta_pest = theta_vmec + lambda (vmec_fieldlines_axisym, utils.py:972-1046); zero_xn_nyq as utils.py:913;
+ *   out [ns*nalpha][ibs_geometry_full_nfields()][nl] in the field order of csrc/ibs_geometry_full.cu (mirrored by
+ *   reference_api.FULL_FIELDS); info_out [ns*nalpha] or NULL: Newton iterations | (not converged) << 16.              */
+int ibs_geometry_full_nfields(void);
+int ibs_geometry_full(const double* tab_mn, const double* tab_nyq, const double* bsupumnc, const double* scal,
+                      const double* xm, const double* xn, const double* xm_nyq, const double* xn_nyq,
+                      int ns, int mnmax, int mnmax_nyq, double phiedge, double aminor_p,
+                      const double* alpha, int nalpha, const double* grid, int nl, int mode, double theta_shift,
+                      int zero_xn_nyq, double phi_center, double* out, int* info_out, void* stream);
+
 /* ---- K2+K3: discretisation + lambda_max + eigenfunction -------------------------------------------
  * Batched gamma_ball_full (utils.py:1550-1624): g, c, f -> half-grid g, second-order finite
  * differences, Dirichlet ends (utils.py:1564-1592) -> largest eigenvalue and eigenvector of
