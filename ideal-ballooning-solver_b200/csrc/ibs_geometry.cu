@@ -27,13 +27,14 @@
 namespace ibs {
 
 constexpr int GEO_THREADS = 128;          // axisymmetric tables: 128-point tiles
-// 3-D tables: ONE CTA of 512 threads per SM (one staged copy of the surface's tables serves 16 warps; 128 registers per
-// thread) and the n-summed Newton coefficients A_m, B_m of every point in shared memory instead of thread-local arrays
+// Round 1's one-point-per-thread 3-D instantiations (kept for comparison, IBS_GEO3D=0).  Measured in round 2: 512-thread
+// CTAs at 128 registers (16 warps / SM) and A_m, B_m in shared memory are 3-9 % SLOWER (NCSX 2.94 -> 3.23 ms, HBERG 92 -> 101 ms):
+// the kernel is bound by the shared-memory data pipe (0.86 wavefronts / clk / SM), not by latency -- see geometry3d_kernel.
 #ifndef IBS_GEO_THREADS_3D
-#define IBS_GEO_THREADS_3D 512
+#define IBS_GEO_THREADS_3D 128
 #endif
 #ifndef IBS_GEO_SMEM_NEWTON
-#define IBS_GEO_SMEM_NEWTON 1
+#define IBS_GEO_SMEM_NEWTON 0
 #endif
 constexpr int GEO_THREADS_3D = IBS_GEO_THREADS_3D;
 constexpr int GEO_SMEM_NEWTON_MAX_M = 16;  // A_m, B_m live in shared memory when mpol + 1 <= this (2 * 16 * 512 * 8 B = 128 KB), else in local memory
@@ -107,6 +108,74 @@ __global__ void pack_nyq_kernel(const double* __restrict__ tab, const int* __res
 template <int SGN> __device__ __forceinline__ void angle(double cm, double sm, double cn, double sn, double& ca, double& sa) {
     if (SGN >= 0) { ca = fma(cm, cn, sm * sn); sa = fma(sm, cn, -(cm * sn)); }      // n >= 0: m th - |n| ph
     else          { ca = fma(cm, cn, -(sm * sn)); sa = fma(sm, cn, cm * sn); }      // n <  0: m th + |n| ph
+}
+
+// The 19 mode sums of one point (utils.py:432-468) handed to the pointwise epilogue
+struct GeoSums {
+    double R, R_s, R_t, R_p, Z_s, Z_t, Z_p, L_s, L_t, L_p;
+    double sqrtg, B, B_s, B_t, B_p, Bsup_p, Bsub_s, Bsub_t, Bsub_p;
+};
+
+// Pointwise algebra of one point (dual basis, grad alpha / psi, drifts, GS2 normalisations: utils.py:474-720) and the
+// stores of its eight base-array entries
+__device__ __forceinline__ void geo_point_epilogue(const GeoParams& p, const GeoSums& gs_, int js, int ja, int jl, double phi, double th,
+                                                   int nit, bool ok, double s_val, double iota, double d_iota, double dpds, double shat) {
+    const double R = gs_.R, R_s = gs_.R_s, R_t = gs_.R_t, R_p = gs_.R_p, Z_s = gs_.Z_s, Z_t = gs_.Z_t, Z_p = gs_.Z_p;
+    const double L_s = gs_.L_s, L_t = gs_.L_t, L_p = gs_.L_p;
+    const double sqrtg = gs_.sqrtg, B = gs_.B, B_s = gs_.B_s, B_t = gs_.B_t, B_p = gs_.B_p, Bsup_p = gs_.Bsup_p;
+    const double Bsub_s = gs_.Bsub_s, Bsub_t = gs_.Bsub_t, Bsub_p = gs_.Bsub_p;
+    // ---- Cartesian dual basis (utils.py:480-508)
+    double sp, cp;
+    sincos(phi, &sp, &cp);
+    const double X_t = R_t * cp, X_p = R_p * cp - R * sp, X_s = R_s * cp;
+    const double Y_t = R_t * sp, Y_p = R_p * sp + R * cp, Y_s = R_s * sp;
+    const double isg = 1.0 / sqrtg;
+    const double gsx = (Y_t * Z_p - Z_t * Y_p) * isg, gsy = (Z_t * X_p - X_t * Z_p) * isg, gsz = (X_t * Y_p - Y_t * X_p) * isg;
+    const double gtx = (Y_p * Z_s - Z_p * Y_s) * isg, gty = (Z_p * X_s - X_p * Z_s) * isg, gtz = (X_p * Y_s - Y_p * X_s) * isg;
+    const double gpx = (Y_s * Z_t - Z_s * Y_t) * isg, gpy = (Z_s * X_t - X_s * Z_t) * isg, gpz = (X_s * Y_t - Y_s * X_t) * isg;
+    // grad psi, grad alpha (utils.py:515-538)
+    const double psi_e = p.psi_e;
+    const double a_s = L_s - (phi - p.phi_center) * d_iota;
+    const double a_t = 1.0 + L_t, a_p = -iota + L_p;
+    const double gax = a_s * gsx + (a_t * gtx + a_p * gpx);
+    const double gay = a_s * gsy + (a_t * gty + a_p * gpy);
+    const double gaz = a_s * gsz + (a_t * gtz + a_p * gpz);
+    const double gqx = gsx * psi_e, gqy = gsy * psi_e, gqz = gsz * psi_e;
+    // drifts (utils.py:603-618, 646-650)
+    const double lpi = L_p - iota;
+    const double BxgB_ga = (Bsub_s * B_t * lpi + Bsub_t * B_p * a_s + Bsub_p * B_s * a_t - Bsub_p * B_t * a_s -
+                            Bsub_t * B_s * lpi - Bsub_s * B_p * a_t) * isg;
+    const double ga_ga = gax * gax + gay * gay + gaz * gaz;
+    const double ga_gq = gax * gqx + gay * gqy + gaz * gqz;
+    const double gq_gq = gqx * gqx + gqy * gqy + gqz * gqz;
+    const double BxgB_gq = (Bsub_t * B_p - Bsub_p * B_t) * isg * psi_e;
+    // GS2 normalisations (utils.py:662-720)
+    const double L_ref = p.L_ref, B_ref = 2.0 * fabs(psi_e) / (L_ref * L_ref);
+    const double sgn = (psi_e > 0.0) ? 1.0 : ((psi_e < 0.0) ? -1.0 : 0.0);
+    const double sqrt_s = sqrt(s_val);
+    const double B3 = B * B * B;
+    const double mu0 = 4.0 * 3.141592653589793 * 1.0e-7;
+    const double bmag = B / B_ref;
+    const double gradpar = L_ref * (iota * Bsup_p) / B;
+    const double gds2 = ga_ga * L_ref * L_ref * s_val;
+    const double gds21 = ga_gq * shat / B_ref;
+    const double gds22 = gq_gq * shat * shat / (L_ref * L_ref * B_ref * B_ref * s_val);
+    const double gbdrift = -1.0 * 2.0 * B_ref * L_ref * L_ref * sqrt_s * BxgB_ga / B3 * sgn;
+    const double gbdrift0 = -1.0 * BxgB_gq * 2.0 * shat / (B3 * sqrt_s) * sgn;
+    const double cvdrift = gbdrift - 2.0 * B_ref * L_ref * L_ref * sqrt_s * mu0 * dpds * sgn / (psi_e * B * B);
+
+    const size_t line = (size_t)js * p.nalpha + ja;
+    double* o = p.base_out + line * IBS_NBASE * p.nl + jl;
+    o[(size_t)IBS_BASE_BMAG * p.nl] = bmag;
+    o[(size_t)IBS_BASE_GRADPAR * p.nl] = gradpar;
+    o[(size_t)IBS_BASE_CVDRIFT * p.nl] = cvdrift;
+    o[(size_t)IBS_BASE_CVDRIFT0 * p.nl] = gbdrift0;      // cvdrift0 = gbdrift0 (utils.py:720)
+    o[(size_t)IBS_BASE_GDS2 * p.nl] = gds2;
+    o[(size_t)IBS_BASE_GDS21 * p.nl] = gds21;
+    o[(size_t)IBS_BASE_GDS22 * p.nl] = gds22;
+    o[(size_t)IBS_BASE_GBDRIFT * p.nl] = gbdrift;
+    if (p.theta_vmec_out) p.theta_vmec_out[line * p.nl + jl] = th;
+    if (p.info_out) atomicMax(p.info_out + line, nit | (ok ? 0 : (1 << 16)));
 }
 
 template <int NT1, int NT2>
@@ -420,58 +489,248 @@ geometry_kernel(const GeoParams p) {
                     cm = cnx;
                 }
             }
-            // ---- Cartesian dual basis (utils.py:480-508)
-            double sp, cp;
-            sincos(phi, &sp, &cp);
-            const double X_t = R_t * cp, X_p = R_p * cp - R * sp, X_s = R_s * cp;
-            const double Y_t = R_t * sp, Y_p = R_p * sp + R * cp, Y_s = R_s * sp;
-            const double isg = 1.0 / sqrtg;
-            const double gsx = (Y_t * Z_p - Z_t * Y_p) * isg, gsy = (Z_t * X_p - X_t * Z_p) * isg, gsz = (X_t * Y_p - Y_t * X_p) * isg;
-            const double gtx = (Y_p * Z_s - Z_p * Y_s) * isg, gty = (Z_p * X_s - X_p * Z_s) * isg, gtz = (X_p * Y_s - Y_p * X_s) * isg;
-            const double gpx = (Y_s * Z_t - Z_s * Y_t) * isg, gpy = (Z_s * X_t - X_s * Z_t) * isg, gpz = (X_s * Y_t - Y_s * X_t) * isg;
-            // grad psi, grad alpha (utils.py:515-538)
-            const double psi_e = p.psi_e;
-            const double a_s = L_s - (phi - p.phi_center) * d_iota;
-            const double a_t = 1.0 + L_t, a_p = -iota + L_p;
-            const double gax = a_s * gsx + (a_t * gtx + a_p * gpx);
-            const double gay = a_s * gsy + (a_t * gty + a_p * gpy);
-            const double gaz = a_s * gsz + (a_t * gtz + a_p * gpz);
-            const double gqx = gsx * psi_e, gqy = gsy * psi_e, gqz = gsz * psi_e;
-            // drifts (utils.py:603-618, 646-650)
-            const double lpi = L_p - iota;
-            const double BxgB_ga = (Bsub_s * B_t * lpi + Bsub_t * B_p * a_s + Bsub_p * B_s * a_t - Bsub_p * B_t * a_s -
-                                    Bsub_t * B_s * lpi - Bsub_s * B_p * a_t) * isg;
-            const double ga_ga = gax * gax + gay * gay + gaz * gaz;
-            const double ga_gq = gax * gqx + gay * gqy + gaz * gqz;
-            const double gq_gq = gqx * gqx + gqy * gqy + gqz * gqz;
-            const double BxgB_gq = (Bsub_t * B_p - Bsub_p * B_t) * isg * psi_e;
-            // GS2 normalisations (utils.py:662-720)
-            const double L_ref = p.L_ref, B_ref = 2.0 * fabs(psi_e) / (L_ref * L_ref);
-            const double sgn = (psi_e > 0.0) ? 1.0 : ((psi_e < 0.0) ? -1.0 : 0.0);
-            const double sqrt_s = sqrt(s_val);
-            const double B3 = B * B * B;
-            const double mu0 = 4.0 * 3.141592653589793 * 1.0e-7;
-            const double bmag = B / B_ref;
-            const double gradpar = L_ref * (iota * Bsup_p) / B;
-            const double gds2 = ga_ga * L_ref * L_ref * s_val;
-            const double gds21 = ga_gq * shat / B_ref;
-            const double gds22 = gq_gq * shat * shat / (L_ref * L_ref * B_ref * B_ref * s_val);
-            const double gbdrift = -1.0 * 2.0 * B_ref * L_ref * L_ref * sqrt_s * BxgB_ga / B3 * sgn;
-            const double gbdrift0 = -1.0 * BxgB_gq * 2.0 * shat / (B3 * sqrt_s) * sgn;
-            const double cvdrift = gbdrift - 2.0 * B_ref * L_ref * L_ref * sqrt_s * mu0 * dpds * sgn / (psi_e * B * B);
+            GeoSums g;
+            g.R = R; g.R_s = R_s; g.R_t = R_t; g.R_p = R_p; g.Z_s = Z_s; g.Z_t = Z_t; g.Z_p = Z_p; g.L_s = L_s; g.L_t = L_t; g.L_p = L_p;
+            g.sqrtg = sqrtg; g.B = B; g.B_s = B_s; g.B_t = B_t; g.B_p = B_p; g.Bsup_p = Bsup_p; g.Bsub_s = Bsub_s; g.Bsub_t = Bsub_t; g.Bsub_p = Bsub_p;
+            geo_point_epilogue(p, g, js, ja, jl, phi, th, nit, ok, s_val, iota, d_iota, dpds, shat);
+        }
+    }
+}
 
-            const size_t line = (size_t)js * p.nalpha + ja;
-            double* o = p.base_out + line * IBS_NBASE * p.nl + jl;
-            o[(size_t)IBS_BASE_BMAG * p.nl] = bmag;
-            o[(size_t)IBS_BASE_GRADPAR * p.nl] = gradpar;
-            o[(size_t)IBS_BASE_CVDRIFT * p.nl] = cvdrift;
-            o[(size_t)IBS_BASE_CVDRIFT0 * p.nl] = gbdrift0;      // cvdrift0 = gbdrift0 (utils.py:720)
-            o[(size_t)IBS_BASE_GDS2 * p.nl] = gds2;
-            o[(size_t)IBS_BASE_GDS21 * p.nl] = gds21;
-            o[(size_t)IBS_BASE_GDS22 * p.nl] = gds22;
-            o[(size_t)IBS_BASE_GBDRIFT * p.nl] = gbdrift;
-            if (p.theta_vmec_out) p.theta_vmec_out[line * p.nl + jl] = th;
-            if (p.info_out) atomicMax(p.info_out + line, nit | (ok ? 0 : (1 << 16)));
+// ---- 3-D equilibria: TWO points per thread ---------------------------------------------------------------------------
+// The paired tables are read with broadcast LDS.128 (E, O): one shared-memory wavefront per FP64 FMA when a thread owns one
+// point, and the SM delivers one wavefront per clock against two DFMA warp-instructions -- round 1's kernel ran the
+// shared-memory data pipe at 85 % of its peak with the FP64 pipe at 60 % (profiles/geometry_r01c_ncsx).  Here a thread
+// owns P = 2 points, so every loaded pair feeds four FMAs, and cos / sin(k nfp phi) are not held as arrays (2 x 28
+// doubles per point would not fit) but advanced inside the k loop by the three-term recurrence
+//     cos((k+1) x) = 2 cos x cos(k x) - cos((k-1) x)       (+2 FMAs per (m, k) and point on 18: the price of the registers)
+// which also makes the toroidal range a run-time loop bound: one kernel for any |n| / nfp.
+#ifndef IBS_GEO3_UNROLL
+#define IBS_GEO3_UNROLL 1
+#endif
+constexpr int GEO3_P = 2;
+constexpr int GEO3_UNROLL = IBS_GEO3_UNROLL;
+constexpr int GEO3_THREADS = 128;
+constexpr int GEO3_SMEM_NEWTON_MAX_M = 16;     // A_m, B_m of both points live in shared memory when mpol + 1 <= this
+
+struct Geo3Point {
+    double theta_p, phi, al, th;
+    int ja, jl, nit; bool ok, valid;
+};
+
+__global__ void __launch_bounds__(GEO3_THREADS, 2)
+geometry3d_kernel(const GeoParams p, const int NT1, const int NT2) {
+    constexpr int P = GEO3_P, T = GEO3_THREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* s_mn = reinterpret_cast<double*>(smem_raw + 16);
+    const int n_mn = p.M1 * (NT1 + 1) * ROWP_MN, n_nyq = p.M2 * (NT2 + 1) * ROWP_NYQ;
+    double* s_nyq = s_mn + n_mn;
+    double* s_ab = s_nyq + n_nyq;                           // [m][A, B][point q][thread]
+    const int tid = threadIdx.x;
+    const int pts_per_surface = p.nalpha * p.nl;
+    const int tiles_per_surface = (pts_per_surface + P * T - 1) / (P * T);
+    unsigned parity = 0;
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    const bool newton_smem = p.M1 <= GEO3_SMEM_NEWTON_MAX_M;
+    double ab_local[2 * MAX_M_NEWTON * P];                  // only touched when mpol is too large for the shared array
+    double* const ab = newton_smem ? (s_ab + tid) : ab_local;
+    const int ab_q = newton_smem ? T : 1, ab_m = newton_smem ? 2 * P * T : 2 * P;       // strides: point, mode
+    const int ab_b = newton_smem ? P * T : P;                                              // A -> B
+
+    const long long W = (long long)p.ns * tiles_per_surface;
+    const long long w_begin = W * blockIdx.x / gridDim.x, w_end = W * (blockIdx.x + 1) / gridDim.x;
+    int js = -1;
+    double s_val = 0, iota = 1, d_iota = 0, dpds = 0, shat = 0;
+    for (long long w = w_begin; w < w_end; ++w) {
+        const int js_w = (int)(w / tiles_per_surface);
+        const int tile = (int)(w - (long long)js_w * tiles_per_surface);
+        if (js_w != js) {
+            js = js_w;
+            __syncthreads();                       // everyone is done with the previous surface's tables
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar, (unsigned)((n_mn + n_nyq) * sizeof(double)));
+                tma_bulk_g2s(s_mn, p.pk_mn + (size_t)js * n_mn, (unsigned)(n_mn * sizeof(double)), bar);
+                tma_bulk_g2s(s_nyq, p.pk_nyq + (size_t)js * n_nyq, (unsigned)(n_nyq * sizeof(double)), bar);
+            }
+            const double* sc = p.scal + (size_t)js * IBS_NSCAL;
+            s_val = sc[0]; iota = sc[1]; d_iota = sc[2]; dpds = sc[3]; shat = sc[4];
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
+        Geo3Point pt[P];
+        double c1p[P], s1p[P];                              // cos / sin(nfp phi)
+        // ---- per point: angles, n-summed Newton coefficients, theta_vmec
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const int ip = tile * (P * T) + q * T + tid;
+            pt[q].valid = ip < pts_per_surface;
+            const int ipc = pt[q].valid ? ip : pts_per_surface - 1;          // (an idle slot repeats the last point; nothing is stored)
+            pt[q].ja = ipc / p.nl; pt[q].jl = ipc - pt[q].ja * p.nl;
+            pt[q].al = p.alpha_per_surface ? p.alpha[(size_t)js * p.nalpha + pt[q].ja] : p.alpha[pt[q].ja];
+            pt[q].theta_p = p.theta[pt[q].jl];
+            pt[q].phi = p.phi_center + (pt[q].theta_p - pt[q].al) / iota;   // utils.py:373
+            sincos((double)p.nfp * pt[q].phi, &s1p[q], &c1p[q]);
+            const double tc = 2.0 * c1p[q];
+            for (int m = 0; m < p.M1; ++m) {
+                const double* row = s_mn + (size_t)m * (NT1 + 1) * ROWP_MN + 12;      // (E, O) of the l row
+                double a = row[0], b = 0.0;
+                double ck = c1p[q], sk = s1p[q], ckm = 1.0, skm = 0.0;
+                for (int k = 1; k <= NT1; ++k) {
+                    const double2 eo = *reinterpret_cast<const double2*>(row + k * ROWP_MN);
+                    a = fma(eo.x, ck, a);
+                    b = fma(eo.y, sk, b);
+                    const double cn = fma(tc, ck, -ckm), sn = fma(tc, sk, -skm);
+                    ckm = ck; skm = sk; ck = cn; sk = sn;
+                }
+                ab[m * ab_m + q * ab_q] = a; ab[m * ab_m + ab_b + q * ab_q] = b;
+            }
+            // Newton:  th + sum_m [ sin(m th) A_m - cos(m th) B_m ] = theta_p   (utils.py:391-416)
+            double th = pt[q].theta_p, dprev = 1e300;
+            int nit; bool ok = false;
+            for (nit = 1; nit <= 25; ++nit) {
+                double s1, c1;
+                sincos(th, &s1, &c1);
+                double cm = 1.0, sm = 0.0, fsum = 0.0, dsum = 0.0;
+                for (int m = 0; m < p.M1; ++m) {
+                    const double a = ab[m * ab_m + q * ab_q], b = ab[m * ab_m + ab_b + q * ab_q];
+                    fsum = fma(sm, a, fsum); fsum = fma(-cm, b, fsum);
+                    const double dm = (double)m;
+                    dsum = fma(dm * cm, a, dsum); dsum = fma(dm * sm, b, dsum);
+                    const double cnx = fma(cm, c1, -(sm * s1));
+                    sm = fma(sm, c1, cm * s1);
+                    cm = cnx;
+                }
+                const double res = (th + fsum) - pt[q].theta_p;
+                const double dth = res / (1.0 + dsum);
+                th -= dth;
+                const double ad = fabs(dth), scale_th = fmax(1.0, fabs(th));
+                if (ad <= 4.5e-16 * scale_th) { ok = true; break; }
+                if (dprev < 1.0 && ad < 1e-3 * dprev) {           // quadratic convergence: see geometry_kernel
+                    const double qq = ad / dprev;
+                    if (ad * qq * qq <= 2e-16 * scale_th) { ok = true; break; }
+                }
+                dprev = ad;
+            }
+            pt[q].th = th; pt[q].nit = nit; pt[q].ok = ok;
+        }
+        // ---- mode sums of both points against ONE stream of table loads (utils.py:420-468)
+        double c1[P], s1[P], tcp[P];
+#pragma unroll
+        for (int q = 0; q < P; ++q) { sincos(pt[q].th, &s1[q], &c1[q]); tcp[q] = 2.0 * c1p[q]; }
+        double R[P], R_s[P], R_t[P], R_p[P], Z_s[P], Z_t[P], Z_p[P], L_s[P], L_t[P], L_p[P];
+        {
+            double cm[P], sm[P];
+#pragma unroll
+            for (int q = 0; q < P; ++q) { cm[q] = 1.0; sm[q] = 0.0; R[q] = R_s[q] = R_t[q] = R_p[q] = Z_s[q] = Z_t[q] = Z_p[q] = L_s[q] = L_t[q] = L_p[q] = 0.0; }
+            for (int m = 0; m < p.M1; ++m) {
+                const double* row = s_mn + (size_t)m * (NT1 + 1) * ROWP_MN;
+                double A[P][9], Bv[P][9], ck[P], sk[P], ckm[P], skm[P];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    const double a0 = row[2 * j];
+#pragma unroll
+                    for (int q = 0; q < P; ++q) { A[q][j] = a0; Bv[q][j] = 0.0; }
+                }
+#pragma unroll
+                for (int q = 0; q < P; ++q) { ck[q] = c1p[q]; sk[q] = s1p[q]; ckm[q] = 1.0; skm[q] = 0.0; }
+#pragma unroll (GEO3_UNROLL)
+                for (int k = 1; k <= NT1; ++k) {
+                    const double* rk = row + k * ROWP_MN;
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) {
+                        const double2 eo = *reinterpret_cast<const double2*>(rk + 2 * j);
+#pragma unroll
+                        for (int q = 0; q < P; ++q) { A[q][j] = fma(eo.x, ck[q], A[q][j]); Bv[q][j] = fma(eo.y, sk[q], Bv[q][j]); }
+                    }
+#pragma unroll
+                    for (int q = 0; q < P; ++q) {
+                        const double cn = fma(tcp[q], ck[q], -ckm[q]), sn = fma(tcp[q], sk[q], -skm[q]);
+                        ckm[q] = ck[q]; skm[q] = sk[q]; ck[q] = cn; sk[q] = sn;
+                    }
+                }
+                // rows: 0 r, 1 n r, 2 r_s, 3 z, 4 n z, 5 z_s, 6 l, 7 n l, 8 l_s
+                const double dm = (double)m;
+#pragma unroll
+                for (int q = 0; q < P; ++q) {
+                    R[q] += fma(cm[q], A[q][0], sm[q] * Bv[q][0]);
+                    R_t[q] = fma(-dm, fma(sm[q], A[q][0], -(cm[q] * Bv[q][0])), R_t[q]);
+                    R_p[q] += fma(sm[q], A[q][1], -(cm[q] * Bv[q][1]));
+                    R_s[q] += fma(cm[q], A[q][2], sm[q] * Bv[q][2]);
+                    Z_t[q] = fma(dm, fma(cm[q], A[q][3], sm[q] * Bv[q][3]), Z_t[q]);
+                    Z_p[q] -= fma(cm[q], A[q][4], sm[q] * Bv[q][4]);
+                    Z_s[q] += fma(sm[q], A[q][5], -(cm[q] * Bv[q][5]));
+                    L_t[q] = fma(dm, fma(cm[q], A[q][6], sm[q] * Bv[q][6]), L_t[q]);
+                    L_p[q] -= fma(cm[q], A[q][7], sm[q] * Bv[q][7]);
+                    L_s[q] += fma(sm[q], A[q][8], -(cm[q] * Bv[q][8]));
+                    const double cnx = fma(cm[q], c1[q], -(sm[q] * s1[q]));
+                    sm[q] = fma(sm[q], c1[q], cm[q] * s1[q]);
+                    cm[q] = cnx;
+                }
+            }
+        }
+        double sqrtg[P], B[P], B_s[P], B_t[P], B_p[P], Bsup_p[P], Bsub_s[P], Bsub_t[P], Bsub_p[P];
+        {
+            double cm[P], sm[P];
+#pragma unroll
+            for (int q = 0; q < P; ++q) { cm[q] = 1.0; sm[q] = 0.0; sqrtg[q] = B[q] = B_s[q] = B_t[q] = B_p[q] = Bsup_p[q] = Bsub_s[q] = Bsub_t[q] = Bsub_p[q] = 0.0; }
+            for (int m = 0; m < p.M2; ++m) {
+                const double* row = s_nyq + (size_t)m * (NT2 + 1) * ROWP_NYQ;
+                double A[P][8], Bv[P][8], ck[P], sk[P], ckm[P], skm[P];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const double a0 = row[2 * j];
+#pragma unroll
+                    for (int q = 0; q < P; ++q) { A[q][j] = a0; Bv[q][j] = 0.0; }
+                }
+#pragma unroll
+                for (int q = 0; q < P; ++q) { ck[q] = c1p[q]; sk[q] = s1p[q]; ckm[q] = 1.0; skm[q] = 0.0; }
+#pragma unroll (GEO3_UNROLL)
+                for (int k = 1; k <= NT2; ++k) {
+                    const double* rk = row + k * ROWP_NYQ;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const double2 eo = *reinterpret_cast<const double2*>(rk + 2 * j);
+#pragma unroll
+                        for (int q = 0; q < P; ++q) { A[q][j] = fma(eo.x, ck[q], A[q][j]); Bv[q][j] = fma(eo.y, sk[q], Bv[q][j]); }
+                    }
+#pragma unroll
+                    for (int q = 0; q < P; ++q) {
+                        const double cn = fma(tcp[q], ck[q], -ckm[q]), sn = fma(tcp[q], sk[q], -skm[q]);
+                        ckm[q] = ck[q]; skm[q] = sk[q]; ck[q] = cn; sk[q] = sn;
+                    }
+                }
+                // rows: 0 g, 1 b, 2 n b, 3 b_s, 4 bsupv, 5 bsubs, 6 bsubu, 7 bsubv
+                const double dm = (double)m;
+#pragma unroll
+                for (int q = 0; q < P; ++q) {
+                    sqrtg[q] += fma(cm[q], A[q][0], sm[q] * Bv[q][0]);
+                    B[q] += fma(cm[q], A[q][1], sm[q] * Bv[q][1]);
+                    B_t[q] = fma(-dm, fma(sm[q], A[q][1], -(cm[q] * Bv[q][1])), B_t[q]);
+                    B_p[q] += fma(sm[q], A[q][2], -(cm[q] * Bv[q][2]));
+                    B_s[q] += fma(cm[q], A[q][3], sm[q] * Bv[q][3]);
+                    Bsup_p[q] += fma(cm[q], A[q][4], sm[q] * Bv[q][4]);
+                    Bsub_s[q] += fma(sm[q], A[q][5], -(cm[q] * Bv[q][5]));
+                    Bsub_t[q] += fma(cm[q], A[q][6], sm[q] * Bv[q][6]);
+                    Bsub_p[q] += fma(cm[q], A[q][7], sm[q] * Bv[q][7]);
+                    const double cnx = fma(cm[q], c1[q], -(sm[q] * s1[q]));
+                    sm[q] = fma(sm[q], c1[q], cm[q] * s1[q]);
+                    cm[q] = cnx;
+                }
+            }
+        }
+        // ---- pointwise algebra and output, one point at a time (utils.py:474-720)
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            if (!pt[q].valid) continue;
+            GeoSums g;
+            g.R = R[q]; g.R_s = R_s[q]; g.R_t = R_t[q]; g.R_p = R_p[q]; g.Z_s = Z_s[q]; g.Z_t = Z_t[q]; g.Z_p = Z_p[q];
+            g.L_s = L_s[q]; g.L_t = L_t[q]; g.L_p = L_p[q];
+            g.sqrtg = sqrtg[q]; g.B = B[q]; g.B_s = B_s[q]; g.B_t = B_t[q]; g.B_p = B_p[q]; g.Bsup_p = Bsup_p[q];
+            g.Bsub_s = Bsub_s[q]; g.Bsub_t = Bsub_t[q]; g.Bsub_p = Bsub_p[q];
+            geo_point_epilogue(p, g, js, pt[q].ja, pt[q].jl, pt[q].phi, pt[q].th, pt[q].nit, pt[q].ok, s_val, iota, d_iota, dpds, shat);
         }
     }
 }
@@ -519,6 +778,28 @@ static int launch_geometry(const GeoParams& p, cudaStream_t st) {
     return IBS_OK;
 }
 
+static int launch_geometry3d(const GeoParams& p, int NT1, int NT2, cudaStream_t st) {
+    const bool newton_smem = p.M1 <= GEO3_SMEM_NEWTON_MAX_M;
+    const size_t smem = 16 + ((size_t)p.M1 * (NT1 + 1) * ROWP_MN + (size_t)p.M2 * (NT2 + 1) * ROWP_NYQ +
+                              (newton_smem ? (size_t)2 * p.M1 * GEO3_P * GEO3_THREADS : 0)) * sizeof(double);
+    if (smem > 220 * 1024) { set_error("Fourier tables of one surface do not fit in shared memory"); return IBS_ERR_UNSUPPORTED; }
+    static bool configured[IBS_MAX_DEVICES] = {false};
+    const int dslot = current_device_slot();
+    if (!configured[dslot]) {
+        IBS_CUDA_CHECK(cudaFuncSetAttribute(geometry3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured[dslot] = true;
+    }
+    int per_sm = 0;
+    IBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, geometry3d_kernel, GEO3_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int tiles = (p.nalpha * p.nl + GEO3_P * GEO3_THREADS - 1) / (GEO3_P * GEO3_THREADS);
+    const long long slots = (long long)num_sms() * per_sm, W = (long long)p.ns * tiles;
+    const int grid = (int)(W < slots ? W : slots);
+    geometry3d_kernel<<<grid, GEO3_THREADS, smem, st>>>(p, NT1, NT2);
+    IBS_CUDA_CHECK(cudaGetLastError());
+    return IBS_OK;
+}
+
 static int gcd_int(int a, int b) { a = std::abs(a); b = std::abs(b); while (b) { int t = a % b; a = b; b = t; } return a; }
 
 int geometry_dispatch(const double* tab_mn, const double* tab_nyq, const double* scal,
@@ -545,12 +826,17 @@ int geometry_dispatch(const double* tab_mn, const double* tab_nyq, const double*
         IBS_REQUIRE(m2[k] >= 0 && std::fabs(xm_nyq[k] - m2[k]) < 1e-9 && std::fabs(xn_nyq[k] - (double)n2[k] * nfp) < 1e-9, "non-integer mode numbers");
         nt2 = std::max(nt2, std::abs(n2[k]));
     }
+    // 3-D tables: the two-points-per-thread kernel takes the toroidal ranges as run-time loop bounds (any |n| / nfp that fits
+    // in shared memory); IBS_GEO3D=0 selects round 1's one-point-per-thread instantiations (|n| / nfp <= 18) for comparison
+    bool use3d = (nt1 > 0 || nt2 > 0);
+    if (const char* e = std::getenv("IBS_GEO3D")) { if (std::atoi(e) == 0) use3d = false; }
     int NT1, NT2;
     if (nt1 == 0 && nt2 == 0) { NT1 = 0; NT2 = 0; }
+    else if (use3d) { NT1 = std::max(nt1, 1); NT2 = std::max(nt2, 1); }
     else if (nt1 <= 6 && nt2 <= 8) { NT1 = 6; NT2 = 8; }
     else if (nt1 <= 11 && nt2 <= 13) { NT1 = 11; NT2 = 13; }
     else if (nt1 <= 16 && nt2 <= 18) { NT1 = 16; NT2 = 18; }
-    else { set_error("toroidal mode range |n|/nfp > 18 is not supported"); return IBS_ERR_UNSUPPORTED; }
+    else { set_error("toroidal mode range |n|/nfp > 18 is not supported by the one-point-per-thread kernels"); return IBS_ERR_UNSUPPORTED; }
     const int M1 = mmax1 + 1, M2 = mmax2 + 1, W1 = 2 * NT1 + 1, W2 = 2 * NT2 + 1;
     if (NT1 > 0 && M1 > MAX_M_NEWTON) { set_error("mpol too large for a 3-D equilibrium"); return IBS_ERR_UNSUPPORTED; }
 
@@ -593,6 +879,7 @@ int geometry_dispatch(const double* tab_mn, const double* tab_nyq, const double*
     if (info_out) IBS_CUDA_CHECK(cudaMemsetAsync(info_out, 0, (size_t)ns * nalpha * sizeof(int), st));
     int rc;
     if (NT1 == 0) rc = launch_geometry<0, 0>(p, st);
+    else if (use3d) rc = launch_geometry3d(p, NT1, NT2, st);
     else if (NT1 == 6) rc = launch_geometry<6, 8>(p, st);
     else if (NT1 == 11) rc = launch_geometry<11, 13>(p, st);
     else rc = launch_geometry<16, 18>(p, st);

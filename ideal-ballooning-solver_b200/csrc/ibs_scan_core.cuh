@@ -41,10 +41,14 @@ namespace scan {
 #define IBS_SCAN_BLK 4
 #endif
 #ifndef IBS_SCAN_BLK_OUT
-#define IBS_SCAN_BLK_OUT IBS_SCAN_BLK
+#define IBS_SCAN_BLK_OUT 2
 #endif
-constexpr int SCAN_BLK = IBS_SCAN_BLK;           // steps per iteration of the iteration pass's loop (2 or 4)
-constexpr int SCAN_BLK_OUT = IBS_SCAN_BLK_OUT;   // ... of the output passes' loops
+// Steps per iteration of the streaming loops.  The loops must stay small: two warps share a scheduler's L0 instruction cache
+// and ncu shows `no_instruction` stalls at EVERY 128-byte line of a loop that does not fit beside its neighbour's (25 % of the
+// samples of a 5.3 KB output-pass loop).  Measured on the bench batch (ms per 303 104 solves, prep included; round 1: 4.72):
+// iteration / output = 2 / 2: 4.24, 4 / 4: 4.32, 4 / 2: 4.23, 2 / 4: 4.28; two inlined copies of the 4-step loops: 5.6.
+constexpr int SCAN_BLK = IBS_SCAN_BLK;           // iteration pass: 4 steps = 2.3 KB (2 steps: 1.2 KB)
+constexpr int SCAN_BLK_OUT = IBS_SCAN_BLK_OUT;   // output passes: 2 steps = 3.0 / 1.9 KB (4 steps: 5.3 / 3.7 KB)
 constexpr int TR = 32;            // records per tile (one pipeline stage holds one forward and one backward tile)
 constexpr int REC = 6;            // doubles per record: G0 G1 G2 (g = G0 + th0 G1 + th0^2 G2), C0 C1 (2 h^2 c), R (2 h^2 f = g R)
 constexpr int MAXLEV = 4;         // coarse levels (strides 2, 4, 8, 16)

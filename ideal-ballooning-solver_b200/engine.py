@@ -133,6 +133,34 @@ def geometry_batch(tables: DeviceTables, alpha, theta, phi_center: float = 0.0, 
     return Geometry(base, dP, thv, info)
 
 
+def geometry_full(st: SurfaceTables, alpha, grid, mode: int = 0, theta_shift: float = 0.0, zero_xn_nyq: bool = False,
+                  phi_center: float = 0.0, device="cuda"):
+    """Every per-point array of the reference's ``vmec_fieldlines`` / ``vmec_fieldlines_axisym`` Struct
+    (``utils.py:723-864``, ``:872-1542``) through ``ibs_geometry_full`` (not a hot kernel).  ``mode`` 0: ``grid`` is
+    theta_pest, 1: phi, 2: theta_vmec (no root solve).  Returns ``(out (ns, nalpha, NF, nl), info (ns, nalpha))``;
+    field order = ``reference_api.FULL_FIELDS``."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    if st.bsupumnc is None:
+        raise ValueError("the full-output geometry needs the bsupumnc table (SurfaceTables.bsupumnc)")
+    dev = torch.device(device)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    tab_mn, tab_nyq, bsu, scal = up(st.tab_mn), up(st.tab_nyq), up(st.bsupumnc), up(st.scal)
+    xm, xn, xmq, xnq = up(st.xm), up(st.xn), up(st.xm_nyq), up(st.xn_nyq)
+    alpha, grid = up(np.atleast_1d(alpha)), up(np.atleast_1d(grid))
+    ns, na, nl = st.ns, alpha.numel(), grid.numel()
+    nf = lib.ibs_geometry_full_nfields()
+    out = torch.empty((ns, na, nf, nl), dtype=torch.float64, device=dev)
+    info = torch.empty((ns, na), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.ibs_geometry_full(_ptr(tab_mn), _ptr(tab_nyq), _ptr(bsu), _ptr(scal), _ptr(xm), _ptr(xn), _ptr(xmq), _ptr(xnq),
+                                   ns, xm.numel(), xmq.numel(), float(st.phiedge), float(st.Aminor_p), _ptr(alpha), na, _ptr(grid), nl,
+                                   int(mode), float(theta_shift), int(bool(zero_xn_nyq)), float(phi_center), _ptr(out), _ptr(info),
+                                   _stream())
+    _lib.check(rc, "ibs_geometry_full")
+    return out, info
+
+
 # ---------------------------------------------------------------------------------------------
 @dataclasses.dataclass
 class Solution:

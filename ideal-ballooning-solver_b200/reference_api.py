@@ -10,9 +10,10 @@ Differences that are deliberate and documented in DESIGN.md:
     ``utils.py:1597``); ``vguess`` is accepted and ignored (no Krylov start vector is needed); ``X`` is
     returned non-negative (the reference's sign is arbitrary, ``utils.py:1605``); ``sigma0`` keeps its
     meaning as a check: if the eigenvalue nearest ``sigma0`` would not be lambda_max a warning is issued.
-  * ``vmec_fieldlines`` returns the quantities the ballooning path reads (``ball_scan.py:254-261``) plus
-    ``theta_vmec``; the remaining ~90 gyrokinetic-geometry arrays of the reference Struct are out of
-    scope.  The ``phi1d`` form raises ``NotImplementedError``.
+  * ``vmec_fieldlines`` / ``vmec_fieldlines_axisym`` return the reference's whole Struct (``utils.py:723-864``,
+    ``:1420-1542``): the per-point arrays come from the full-output geometry kernel (``ibs_geometry_full``), the
+    per-surface scalars from the radial splines; ``theta_vmec`` is the converged root (the reference stops scipy's secant
+    iteration at 1.48e-8).  ``plot=True`` raises ``NotImplementedError``.
 """
 from __future__ import annotations
 
@@ -23,7 +24,27 @@ import numpy as np
 
 from . import engine, tables
 
-__all__ = ["vmec_splines", "vmec_fieldlines", "gamma_ball_full", "obj_w_grad", "Struct"]
+__all__ = ["vmec_splines", "vmec_fieldlines", "vmec_fieldlines_axisym", "gamma_ball_full", "obj_w_grad", "derm", "dermv", "Struct",
+           "FULL_FIELDS"]
+
+#: per-point arrays written by ``ibs_geometry_full``, in the order of the enum in ``csrc/ibs_geometry_full.cu``
+FULL_FIELDS = (
+    "phi", "theta_pest", "theta_vmec", "lambdas",
+    "R", "d_R_d_s", "d_R_d_theta_vmec", "d_R_d_phi", "Z", "d_Z_d_s", "d_Z_d_theta_vmec", "d_Z_d_phi",
+    "d_lambda_d_s", "d_lambda_d_theta_vmec", "d_lambda_d_phi",
+    "sqrt_g_vmec", "modB", "d_B_d_s", "d_B_d_theta_vmec", "d_B_d_phi", "B_sup_theta_vmec", "B_sup_phi",
+    "B_sub_s", "B_sub_theta_vmec", "B_sub_phi", "B_sup_theta_pest", "sqrt_g_vmec_alt", "sinphi", "cosphi",
+    "d_X_d_theta_vmec", "d_X_d_phi", "d_X_d_s", "d_Y_d_theta_vmec", "d_Y_d_phi", "d_Y_d_s",
+    "grad_s_X", "grad_s_Y", "grad_s_Z", "grad_theta_vmec_X", "grad_theta_vmec_Y", "grad_theta_vmec_Z",
+    "grad_phi_X", "grad_phi_Y", "grad_phi_Z", "grad_psi_X", "grad_psi_Y", "grad_psi_Z",
+    "grad_alpha_X", "grad_alpha_Y", "grad_alpha_Z", "grad_B_X", "grad_B_Y", "grad_B_Z", "B_X", "B_Y", "B_Z",
+    "B_cross_grad_s_dot_grad_alpha", "B_cross_grad_s_dot_grad_alpha_alternate",
+    "B_cross_grad_B_dot_grad_alpha", "B_cross_grad_B_dot_grad_alpha_alternate",
+    "B_cross_grad_B_dot_grad_psi", "B_cross_kappa_dot_grad_psi", "B_cross_kappa_dot_grad_alpha",
+    "grad_alpha_dot_grad_alpha", "grad_alpha_dot_grad_psi", "grad_psi_dot_grad_psi",
+    "bmag", "gradpar_theta_pest", "gradpar_phi", "gds2", "gds21", "gds22", "gbdrift", "gbdrift0", "cvdrift", "cvdrift0",
+    "B_p",
+)
 
 DEL_ALPHA = 0.004          # utils.py:1639
 
@@ -49,26 +70,69 @@ def _as_splines(vs):
     return vmec_splines(vs)            # utils.py:272-274: a Vmec object is converted on the fly
 
 
-def vmec_fieldlines(vs, s, alpha, theta1d=None, phi1d=None, phi_center=0, plot=False, show=True):
-    """``vmec_fieldlines`` (``utils.py:161-864``), hot-path subset, arrays shaped ``(ns, nalpha, nl)``."""
+def _struct_common(out, vs, st, s, alpha, theta1d, phi1d, phi_center, fields, skip=()):
+    """Per-surface scalars and bookkeeping entries of the Struct (``utils.py:723-760, 846-864``) + the per-point arrays."""
+    out.ns, out.nalpha = len(s), len(alpha)
+    out.nl = len(theta1d) if theta1d is not None else len(phi1d)
+    out.s, out.alpha, out.theta1d, out.phi1d = s, alpha, theta1d, phi1d
+    out.iota, out.d_iota_d_s = st.row("iota"), st.row("d_iota_d_s")
+    out.d_pressure_d_s, out.shat = st.row("d_pressure_d_s"), st.row("shat")
+    out.phi_center = phi_center
+    psi_e = -st.phiedge / (2 * np.pi)                                 # utils.py:474
+    out.edge_toroidal_flux_over_2pi = psi_e
+    out.L_reference = st.Aminor_p                                     # utils.py:662-664
+    out.B_reference = 2 * abs(psi_e) / (st.Aminor_p * st.Aminor_p)
+    out.toroidal_flux_sign = np.sign(psi_e)
+    pres = st.row("pressure")
+    sqrt_s = np.sqrt(s)
+    out.beta_N = 4 * np.pi * 1e-7 * pres / out.B_reference ** 2       # utils.py:668-676
+    out.tprim = -1 * out.d_pressure_d_s * 2 * sqrt_s * 2 / 3 * 1 / pres
+    out.fprim = -1 * out.d_pressure_d_s * 2 * sqrt_s * 1 / 3 * 1 / pres
+    out.temp = pres ** (2 / 3)
+    out.dens = pres ** (1 / 3)
+    for k, name in enumerate(FULL_FIELDS):
+        if name not in skip:
+            setattr(out, name, np.ascontiguousarray(fields[:, :, k, :]))
+    return out
+
+
+def _surface_tables(vs, s):
     vs = _as_splines(vs)
+    return vs if isinstance(vs, tables.SurfaceTables) else vs.evaluate(s)
+
+
+def vmec_fieldlines(vs, s, alpha, theta1d=None, phi1d=None, phi_center=0, plot=False, show=True):
+    """``vmec_fieldlines`` (``utils.py:161-864``): the whole Struct, arrays shaped ``(ns, nalpha, nl)``."""
     s = np.atleast_1d(np.asarray(s, dtype=np.float64))             # utils.py:277-291
     alpha = np.atleast_1d(np.asarray(alpha, dtype=np.float64))
     if (theta1d is not None) and (phi1d is not None):
         raise ValueError("You cannot specify both theta and phi")   # utils.py:293-294
     if (theta1d is None) and (phi1d is None):
         raise ValueError("You must specify either theta or phi")    # utils.py:295-296
-    if theta1d is None:
-        raise NotImplementedError("vmec_fieldlines(phi1d=...) is outside the ballooning hot path")
     if plot:
         raise NotImplementedError("plotting is outside the ballooning hot path")
-    theta1d = np.asarray(theta1d, dtype=np.float64)
-    st = vs if isinstance(vs, tables.SurfaceTables) else vs.evaluate(s)
+    st = _surface_tables(vs, s)
+    grid = np.asarray(theta1d if theta1d is not None else phi1d, dtype=np.float64)
+    if st.bsupumnc is None:
+        # tables without bsupumnc (e.g. built by hand for the hot path): the eight hot-path arrays from K1
+        if theta1d is None:
+            raise ValueError("vmec_fieldlines(phi1d=...) needs the full tables (bsupumnc)")
+        return _fieldlines_hot(st, s, alpha, grid, phi_center)
+    fields, info = engine.geometry_full(st, alpha, grid, mode=0 if theta1d is not None else 1, phi_center=float(phi_center))
+    if np.any(info.cpu().numpy() >> 16):
+        # the reference's scipy.optimize.newton raises RuntimeError when the root solve fails (utils.py:410)
+        raise RuntimeError("Failed to converge: theta_vmec root solve")
+    out = _struct_common(Struct(), vs, st, s, alpha, None if theta1d is None else grid, None if phi1d is None else grid,
+                         phi_center, fields.cpu().numpy(), skip=("lambdas", "B_p"))
+    out.dPdrho = -1.0 * 0.5 * np.mean((out.cvdrift - out.gbdrift) * out.bmag ** 2, axis=-1)   # ball_scan.py:262 (convenience)
+    return out
+
+
+def _fieldlines_hot(st, s, alpha, theta1d, phi_center):
+    """The hot-path subset through K1 (``ibs_geometry_batch``): the eight arrays ``ball_scan.py:254-261`` reads."""
     dt = engine.DeviceTables.from_host(st)
     geo = engine.geometry_batch(dt, alpha, theta1d, phi_center=float(phi_center), want_theta_vmec=True, want_info=True)
-    info = geo.info.cpu().numpy()
-    if np.any(info >> 16):
-        # the reference's scipy.optimize.newton raises RuntimeError when the root solve fails (utils.py:410)
+    if np.any(geo.info.cpu().numpy() >> 16):
         raise RuntimeError("Failed to converge: theta_vmec root solve")
     base = geo.base.cpu().numpy()
     out = Struct()
@@ -84,6 +148,54 @@ def vmec_fieldlines(vs, s, alpha, theta1d=None, phi1d=None, phi_center=0, plot=F
         setattr(out, name, np.ascontiguousarray(base[:, :, k, :]))
     out.gbdrift0 = out.cvdrift0                                      # utils.py:720
     out.dPdrho = geo.dPdrho.cpu().numpy()                            # ball_scan.py:262 (convenience, not in the reference Struct)
+    return out
+
+
+def vmec_fieldlines_axisym(vs, s, alpha, theta1d=None, phi1d=None, phi_center=0, plot=False, show=True):
+    """``vmec_fieldlines_axisym`` (``utils.py:872-1542``): the axisymmetric routine the boundary-curvature penalty uses
+    (``Simsopt_runner.py:231-245``).  A uniform theta_vmec grid spanning ``theta1d`` (no root solve, ``:972-978``), the
+    poloidal angle flipped by pi when the first step along the grid is not counter-clockwise from the inboard side
+    (``:993-1010``), ``theta_pest = theta_vmec + lambda`` (``:1043``), and the ``*_1`` arrays interpolated back onto
+    ``theta1d`` from the first surface / field line (``:1333-1369``)."""
+    s = np.atleast_1d(np.asarray(s, dtype=np.float64))
+    alpha = np.atleast_1d(np.asarray(alpha, dtype=np.float64))
+    if (theta1d is not None) and (phi1d is not None):
+        raise ValueError("You cannot specify both theta and phi")   # utils.py:901-902
+    if (theta1d is None) and (phi1d is None):
+        raise ValueError("You must specify either theta or phi")    # utils.py:903-904
+    if theta1d is None:
+        raise TypeError("vmec_fieldlines_axisym needs theta1d (the reference dereferences it unconditionally, utils.py:976)")
+    if plot:
+        raise NotImplementedError("plotting is outside the ballooning hot path")
+    theta1d = np.asarray(theta1d, dtype=np.float64)
+    st = _surface_tables(vs, s)
+    if st.bsupumnc is None:
+        raise ValueError("vmec_fieldlines_axisym needs the full tables (bsupumnc)")
+    theta_v = np.linspace(np.min(theta1d), np.max(theta1d), len(theta1d))             # utils.py:972-978
+    # orientation test on the first two points of the first surface (utils.py:984-1001), at phi = 0
+    ang = st.xm[:, None] * theta_v[None, :2]
+    R2 = st.tab_mn[0, 0] @ np.cos(ang)
+    Z2 = st.tab_mn[0, 1] @ np.sin(ang)
+    flipit = bool(R2[0] > R2[1] or Z2[1] > Z2[0])
+    fields, _ = engine.geometry_full(st, alpha, theta_v, mode=2, theta_shift=np.pi if flipit else 0.0, zero_xn_nyq=True,
+                                     phi_center=float(phi_center))
+    F = fields.cpu().numpy()
+    out = _struct_common(Struct(), vs, st, s, alpha, theta1d, phi1d, phi_center, F, skip=("lambdas", "B_p"))
+    B_p = F[:, :, FULL_FIELDS.index("B_p"), :]                       # utils.py:1282-1286
+    # the `_1` arrays: first surface, first field line, interpolated from theta_pest back to theta1d (utils.py:1333-1369)
+    tp = out.theta_pest[0][0]
+    on_grid = lambda a: np.interp(theta1d, tp, a[0][0])
+    out.cvdrift0_1 = on_grid(out.cvdrift0)
+    out.gbdrift0_1 = on_grid(out.cvdrift0)
+    out.gradpar_theta_pest_1 = on_grid(out.gradpar_theta_pest)
+    out.bmag_1, out.B_p_1 = on_grid(out.bmag), on_grid(B_p)
+    out.cvdrift_1, out.gbdrift_1 = on_grid(out.cvdrift), on_grid(out.gbdrift)
+    out.gds21_1, out.gds22_1, out.gds2_1 = on_grid(out.gds21), on_grid(out.gds22), on_grid(out.gds2)
+    out.R_1, out.Z_1 = on_grid(out.R), on_grid(out.Z)
+    psi_e = out.edge_toroidal_flux_over_2pi
+    out.Rprime_1 = on_grid(out.d_R_d_s) * 1 / psi_e * 1 / out.iota * out.R_1 * out.B_p_1
+    out.Zprime_1 = on_grid(out.d_Z_d_s) * 1 / psi_e * 1 / out.iota * out.R_1 * out.B_p_1
+    out.loc_shr = out.gds21_1 * 0                                    # utils.py:1392
     return out
 
 

@@ -41,6 +41,8 @@ class SurfaceTables:
     phiedge: float
     Aminor_p: float
     nfp: int
+    bsupumnc: np.ndarray = None     # (ns, mnmax_nyq): only the full-output geometry needs it (B_sup_theta_vmec, utils.py:460)
+    raxis_cc: np.ndarray = None     # magnetic-axis Fourier coefficients (utils.py:1032, axisymmetric routine)
 
     @property
     def ns(self):
@@ -61,7 +63,8 @@ class SurfaceTables:
         idx = np.atleast_1d(idx)
         return dataclasses.replace(self, tab_mn=np.ascontiguousarray(self.tab_mn[idx]),
                                    tab_nyq=np.ascontiguousarray(self.tab_nyq[idx]),
-                                   scal=np.ascontiguousarray(self.scal[idx]))
+                                   scal=np.ascontiguousarray(self.scal[idx]),
+                                   bsupumnc=None if self.bsupumnc is None else np.ascontiguousarray(self.bsupumnc[idx]))
 
 
 class RadialSplines:
@@ -80,6 +83,8 @@ class RadialSplines:
         # utils.py:82-107 (bsubsmns is on the full mesh, the others on the half mesh)
         self.gmnc, self.bmnc = half(w.gmnc), half(w.bmnc)
         self.bsupvmnc = half(w.bsupvmnc)
+        self.bsupumnc = half(w.bsupumnc) if hasattr(w, "bsupumnc") else None
+        self.raxis_cc = np.asarray(w.raxis_cc, float) if hasattr(w, "raxis_cc") else None
         self.bsubsmns = full(w.bsubsmns)
         self.bsubumnc, self.bsubvmnc = half(w.bsubumnc), half(w.bsubvmnc)
         # utils.py:110-119
@@ -111,7 +116,9 @@ class RadialSplines:
         scal[:, 4] = (-2 * s / iota) * diota            # shat, utils.py:316
         scal[:, 5] = self.pressure(s)
         return SurfaceTables(tab_mn, tab_nyq, scal, self.xm, self.xn, self.xm_nyq, self.xn_nyq,
-                             self.phiedge, self.Aminor_p, self.nfp)
+                             self.phiedge, self.Aminor_p, self.nfp,
+                             bsupumnc=None if self.bsupumnc is None else np.ascontiguousarray(self.bsupumnc(s)),
+                             raxis_cc=self.raxis_cc)
 
 
 _TABLES_2D = ["rmnc", "zmns", "lmns", "gmnc", "bmnc", "bsupumnc", "bsupvmnc",

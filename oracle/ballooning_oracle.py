@@ -145,6 +145,134 @@ def fieldlines(tab, alpha, theta1d, phi_center=0.0, full=False):
     return out
 
 
+# ---------------------------------------------------------------------------------------
+# f4: the whole Struct of vmec_fieldlines (utils.py:161-864) and of vmec_fieldlines_axisym (utils.py:872-1542)
+# ---------------------------------------------------------------------------------------
+def fieldlines_full(tab, alpha, theta1d=None, phi1d=None, phi_center=0.0, axisym=False):
+    """Restatement of the full-output geometry: every per-point array of the Struct the reference returns
+    (``utils.py:723-864``), for ``vmec_fieldlines(theta1d=...)``, ``vmec_fieldlines(phi1d=...)`` (``:364-373``) and -- with
+    ``axisym=True`` -- ``vmec_fieldlines_axisym`` (uniform theta_vmec, orientation flip, ``theta_pest = theta_vmec +
+    lambda``, the ``*_1`` arrays interpolated back to ``theta1d``: ``:972-1046, 1282-1369``).  ``tab`` must carry the
+    ``bsupumnc`` table.  Vectors are kept as ``(3, ns, nalpha, nl)`` arrays."""
+    alpha = np.atleast_1d(np.asarray(alpha, dtype=float))
+    s, iota, d_iota = tab.row("s"), tab.row("iota"), tab.row("d_iota_d_s")
+    dpds, shat = tab.row("d_pressure_d_s"), tab.row("shat")
+    io, dio = iota[:, None, None], d_iota[:, None, None]
+    ns, na = s.size, alpha.size
+    xm, xn, xmq = tab.xm, tab.xn, tab.xm_nyq
+    xnq = np.zeros_like(tab.xn_nyq) if axisym else tab.xn_nyq            # utils.py:913
+    lmns = tab.row("lmns")
+    if axisym:
+        theta1d = np.asarray(theta1d, dtype=float)
+        nl = theta1d.size
+        theta_vmec = np.broadcast_to(np.linspace(theta1d.min(), theta1d.max(), nl), (ns, na, nl)).copy()     # utils.py:972-978
+        phi_sum = np.zeros((ns, na, nl))                                  # phi is still zero when the angles are formed
+        a0 = xm[:, None] * theta_vmec[0, 0, :2][None]
+        R2, Z2 = tab.row("rmnc")[0] @ np.cos(a0), tab.row("zmns")[0] @ np.sin(a0)
+        shift = np.pi if (R2[0] > R2[1] or Z2[1] > Z2[0]) else 0.0        # utils.py:993-1010
+    else:
+        shift = 0.0
+        if theta1d is not None:
+            theta1d = np.asarray(theta1d, dtype=float)
+            nl = theta1d.size
+            theta_pest = np.broadcast_to(theta1d, (ns, na, nl)).copy()
+            phi = phi_center + (theta1d[None, None, :] - alpha[None, :, None]) / io                          # utils.py:371-373
+        else:
+            phi1d = np.asarray(phi1d, dtype=float)
+            nl = phi1d.size
+            phi = np.broadcast_to(phi1d, (ns, na, nl)).copy()
+            theta_pest = alpha[None, :, None] + io * (phi1d[None, None, :] - phi_center)                     # utils.py:364-369
+        theta_vmec = np.empty((ns, na, nl))
+        for js in range(ns):                                              # utils.py:391-416
+            res = lambda tv, p0, tgt: tgt - (tv + np.sum(lmns[js, :, None] * np.sin(xm[:, None] * tv - xn[:, None] * p0), axis=0))
+            for ja in range(na):
+                theta_vmec[js, ja] = newton(res, x0=theta_pest[js, ja], x1=theta_pest[js, ja] + 0.1, args=(phi[js, ja], theta_pest[js, ja]))
+        phi_sum = phi
+
+    def modesum(coef, m, n, kind, weight=None):
+        ang = m[:, None, None, None] * (theta_vmec[None] + shift) - n[:, None, None, None] * phi_sum[None]
+        basis = np.cos(ang) if kind == "c" else np.sin(ang)
+        if weight is not None:
+            basis = weight[:, None, None, None] * basis
+        return np.einsum("ij,jikl->ikl", tab.row(coef) if isinstance(coef, str) else coef, basis)
+
+    o = types.SimpleNamespace(ns=ns, nalpha=na, nl=nl, theta_vmec=theta_vmec)
+    # utils.py:432-468
+    o.R, o.d_R_d_s = modesum("rmnc", xm, xn, "c"), modesum("d_rmnc_d_s", xm, xn, "c")
+    o.d_R_d_theta_vmec, o.d_R_d_phi = -modesum("rmnc", xm, xn, "s", xm), modesum("rmnc", xm, xn, "s", xn)
+    o.Z, o.d_Z_d_s = modesum("zmns", xm, xn, "s"), modesum("d_zmns_d_s", xm, xn, "s")
+    o.d_Z_d_theta_vmec, o.d_Z_d_phi = modesum("zmns", xm, xn, "c", xm), -modesum("zmns", xm, xn, "c", xn)
+    lambdas = modesum("lmns", xm, xn, "s")
+    o.d_lambda_d_s = modesum("d_lmns_d_s", xm, xn, "s")
+    o.d_lambda_d_theta_vmec, o.d_lambda_d_phi = modesum("lmns", xm, xn, "c", xm), -modesum("lmns", xm, xn, "c", xn)
+    if axisym:
+        theta_pest = theta_vmec + lambdas                                 # utils.py:1043
+        phi = phi_center + (theta_pest - alpha[None, :, None]) / io       # utils.py:1046
+    o.theta_pest, o.phi = theta_pest, phi
+    o.sqrt_g_vmec, o.modB, o.d_B_d_s = modesum("gmnc", xmq, xnq, "c"), modesum("bmnc", xmq, xnq, "c"), modesum("d_bmnc_d_s", xmq, xnq, "c")
+    o.d_B_d_theta_vmec, o.d_B_d_phi = -modesum("bmnc", xmq, xnq, "s", xmq), modesum("bmnc", xmq, xnq, "s", xnq)
+    o.B_sup_theta_vmec, o.B_sup_phi = modesum(tab.bsupumnc, xmq, xnq, "c"), modesum("bsupvmnc", xmq, xnq, "c")
+    o.B_sub_s, o.B_sub_theta_vmec, o.B_sub_phi = modesum("bsubsmns", xmq, xnq, "s"), modesum("bsubumnc", xmq, xnq, "c"), modesum("bsubvmnc", xmq, xnq, "c")
+    o.B_sup_theta_pest = io * o.B_sup_phi
+    o.sqrt_g_vmec_alt = o.R * (o.d_Z_d_s * o.d_R_d_theta_vmec - o.d_R_d_s * o.d_Z_d_theta_vmec)
+    psi_e = -tab.phiedge / (2 * np.pi)
+    o.edge_toroidal_flux_over_2pi = psi_e
+    # utils.py:480-508: covariant basis in Cartesian components, dual relations
+    o.sinphi, o.cosphi = np.sin(phi), np.cos(phi)
+    e_t = np.stack([o.d_R_d_theta_vmec * o.cosphi, o.d_R_d_theta_vmec * o.sinphi, o.d_Z_d_theta_vmec])
+    e_p = np.stack([o.d_R_d_phi * o.cosphi - o.R * o.sinphi, o.d_R_d_phi * o.sinphi + o.R * o.cosphi, o.d_Z_d_phi])
+    e_s = np.stack([o.d_R_d_s * o.cosphi, o.d_R_d_s * o.sinphi, o.d_Z_d_s])
+    for nm, v in (("theta_vmec", e_t), ("phi", e_p), ("s", e_s)):
+        setattr(o, f"d_X_d_{nm}", v[0]); setattr(o, f"d_Y_d_{nm}", v[1])
+    cr = lambda a, b: np.cross(a, b, axis=0)
+    grad_s, grad_t, grad_p = cr(e_t, e_p) / o.sqrt_g_vmec, cr(e_p, e_s) / o.sqrt_g_vmec, cr(e_s, e_t) / o.sqrt_g_vmec
+    grad_psi = grad_s * psi_e
+    a_s = o.d_lambda_d_s - (phi - phi_center) * dio                       # utils.py:519-538
+    a_t, a_p = 1 + o.d_lambda_d_theta_vmec, -io + o.d_lambda_d_phi
+    grad_alpha = a_s * grad_s + (a_t * grad_t + a_p * grad_p)
+    grad_B = o.d_B_d_s * grad_s + o.d_B_d_theta_vmec * grad_t + o.d_B_d_phi * grad_p
+    Bvec = psi_e * (a_t * e_p + (io - o.d_lambda_d_phi) * e_t) / o.sqrt_g_vmec                               # utils.py:555-577
+    for nm, v in (("grad_s", grad_s), ("grad_theta_vmec", grad_t), ("grad_phi", grad_p), ("grad_psi", grad_psi),
+                  ("grad_alpha", grad_alpha), ("grad_B", grad_B), ("B", Bvec)):
+        for k, ax in enumerate("XYZ"):
+            setattr(o, f"{nm}_{ax}", v[k])
+    dt = lambda a, b: np.sum(a * b, axis=0)
+    lpi = o.d_lambda_d_phi - io
+    o.B_cross_grad_s_dot_grad_alpha = (o.B_sub_phi * a_t - o.B_sub_theta_vmec * lpi) / o.sqrt_g_vmec          # utils.py:588-591
+    o.B_cross_grad_s_dot_grad_alpha_alternate = dt(Bvec, cr(grad_s, grad_alpha))
+    o.B_cross_grad_B_dot_grad_alpha = (o.B_sub_s * o.d_B_d_theta_vmec * lpi + o.B_sub_theta_vmec * o.d_B_d_phi * a_s
+                                       + o.B_sub_phi * o.d_B_d_s * a_t - o.B_sub_phi * o.d_B_d_theta_vmec * a_s
+                                       - o.B_sub_theta_vmec * o.d_B_d_s * lpi - o.B_sub_s * o.d_B_d_phi * a_t) / o.sqrt_g_vmec
+    o.B_cross_grad_B_dot_grad_alpha_alternate = dt(Bvec, cr(grad_B, grad_alpha))
+    o.grad_alpha_dot_grad_alpha, o.grad_alpha_dot_grad_psi, o.grad_psi_dot_grad_psi = dt(grad_alpha, grad_alpha), dt(grad_alpha, grad_psi), dt(grad_psi, grad_psi)
+    o.B_cross_grad_B_dot_grad_psi = (o.B_sub_theta_vmec * o.d_B_d_phi - o.B_sub_phi * o.d_B_d_theta_vmec) / o.sqrt_g_vmec * psi_e
+    o.B_cross_kappa_dot_grad_psi = o.B_cross_grad_B_dot_grad_psi / o.modB
+    o.B_cross_kappa_dot_grad_alpha = o.B_cross_grad_B_dot_grad_alpha / o.modB + MU0 * dpds[:, None, None] / psi_e
+    # utils.py:662-720
+    L_ref = tab.Aminor_p
+    B_ref = 2 * abs(psi_e) / (L_ref * L_ref)
+    sgn, sqrt_s, s3, sh = np.sign(psi_e), np.sqrt(s)[:, None, None], s[:, None, None], shat[:, None, None]
+    o.L_reference, o.B_reference, o.toroidal_flux_sign = L_ref, B_ref, sgn
+    o.bmag, o.gradpar_theta_pest, o.gradpar_phi = o.modB / B_ref, L_ref * o.B_sup_theta_pest / o.modB, L_ref * o.B_sup_phi / o.modB
+    o.gds2 = o.grad_alpha_dot_grad_alpha * L_ref * L_ref * s3
+    o.gds21 = o.grad_alpha_dot_grad_psi * sh / B_ref
+    o.gds22 = o.grad_psi_dot_grad_psi * sh * sh / (L_ref * L_ref * B_ref * B_ref * s3)
+    o.gbdrift = -1.0 * 2 * B_ref * L_ref * L_ref * sqrt_s * o.B_cross_grad_B_dot_grad_alpha / o.modB ** 3 * sgn
+    o.gbdrift0 = -1.0 * o.B_cross_grad_B_dot_grad_psi * 2 * sh / (o.modB ** 3 * sqrt_s) * sgn
+    o.cvdrift = o.gbdrift - 2 * B_ref * L_ref * L_ref * sqrt_s * MU0 * dpds[:, None, None] * sgn / (psi_e * o.modB * o.modB)
+    o.cvdrift0 = o.gbdrift0
+    if axisym:                                                           # utils.py:1282-1286, 1333-1392
+        B_p = np.sqrt(o.B_sub_theta_vmec * abs(psi_e) * io)
+        back = lambda a: np.interp(theta1d, theta_pest[0][0], a[0][0])
+        for nm in ("gradpar_theta_pest", "bmag", "cvdrift", "gbdrift", "gds21", "gds22", "gds2", "R", "Z"):
+            setattr(o, nm + "_1", back(getattr(o, nm)))
+        o.cvdrift0_1 = o.gbdrift0_1 = back(o.cvdrift0)
+        o.B_p_1 = back(B_p)
+        o.Rprime_1 = back(o.d_R_d_s) / psi_e / iota * o.R_1 * o.B_p_1
+        o.Zprime_1 = back(o.d_Z_d_s) / psi_e / iota * o.R_1 * o.B_p_1
+    return o
+
+
 def dpdrho_of(fl, js=0, ja=0):
     """``dPdrho = -0.5*mean((cvdrift-gbdrift)*bmag**2)`` (``ball_scan.py:262``, ``utils.py:1657``)."""
     return -1.0 * 0.5 * np.mean((fl.cvdrift[js][ja] - fl.gbdrift[js][ja]) * fl.bmag[js][ja] ** 2)

@@ -97,3 +97,12 @@ def test_product_does_not_import_oracle():
         if os.path.isfile(p):
             code = "\n".join(ln for ln in open(p).read().splitlines() if "open(" in ln or "import" in ln)
             assert "/root/reference" not in code
+
+
+def test_layout_constants_match_the_python_mirrors():
+    """Pure host queries of the library (no GPU needed): the field list of the full-output geometry and the size of the refine state."""
+    from ideal_ballooning_solver_b200 import _lib, reference_api
+    lib = _lib.load(build_if_missing=True)
+    assert lib.ibs_geometry_full_nfields() == len(reference_api.FULL_FIELDS)
+    assert len(set(reference_api.FULL_FIELDS)) == len(reference_api.FULL_FIELDS)
+    assert lib.ibs_refine_state_doubles() == 30

@@ -148,3 +148,33 @@ def test_derm_dermv_restatement_matches_reference_golden(golden):
         assert r.shape == G[key].shape and np.array_equal(r, G[key]), key
         n += 1
     assert n == 14
+
+
+@pytest.mark.parametrize("case", ["fl_theta", "fl_phi", "axisym"])
+def test_full_struct_restatement_matches_reference_fixture(golden, case):
+    """f4: the oracle's restatement of the whole vmec_fieldlines / vmec_fieldlines_axisym Struct against the fixture the
+    unmodified reference produced (tests/golden/make_golden_full.py)."""
+    from ideal_ballooning_solver_b200.tables import SurfaceTables
+    D = golden("full_struct")
+    g = lambda k: np.array(D[f"{case}__in_{k}"])
+    st = SurfaceTables(g("tab_mn"), g("tab_nyq"), g("scal"), g("xm"), g("xn"), g("xm_nyq"), g("xn_nyq"), float(g("phiedge")),
+                       float(g("Aminor_p")), int(g("nfp")), bsupumnc=g("bsupumnc"), raxis_cc=g("raxis_cc"))
+    kw = dict(phi_center=float(g("phi_center")))
+    if case == "fl_phi":
+        kw["phi1d"] = g("phi1d")
+    else:
+        kw["theta1d"] = g("theta1d")
+    o = bo.fieldlines_full(st, g("alpha"), axisym=(case == "axisym"), **kw)
+    n = 0
+    for key in D.files:
+        if not key.startswith(case + "__") or key.startswith(case + "__in_"):
+            continue
+        name = key[len(case) + 2:]
+        if not hasattr(o, name):
+            continue                    # per-surface scalars and bookkeeping entries are formed by the facade, not here
+        want, got = np.asarray(D[key]), np.asarray(getattr(o, name), dtype=float)
+        assert got.shape == want.shape, name
+        scale = max(float(np.max(np.abs(want))), 1e-300)
+        assert float(np.max(np.abs(got - want))) / scale < (2e-9 if name.endswith("_alternate") else 1e-11), (case, name)
+        n += 1
+    assert n >= (85 if case == "axisym" else 75)
