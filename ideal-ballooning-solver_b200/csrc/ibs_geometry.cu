@@ -497,14 +497,19 @@ geometry_kernel(const GeoParams p) {
     }
 }
 
-// ---- 3-D equilibria: TWO points per thread ---------------------------------------------------------------------------
+// ---- 3-D equilibria: TWO points per thread (any toroidal range; NOT the default) ---------------------------------------
 // The paired tables are read with broadcast LDS.128 (E, O): one shared-memory wavefront per FP64 FMA when a thread owns one
-// point, and the SM delivers one wavefront per clock against two DFMA warp-instructions -- round 1's kernel ran the
-// shared-memory data pipe at 85 % of its peak with the FP64 pipe at 60 % (profiles/geometry_r01c_ncsx).  Here a thread
-// owns P = 2 points, so every loaded pair feeds four FMAs, and cos / sin(k nfp phi) are not held as arrays (2 x 28
-// doubles per point would not fit) but advanced inside the k loop by the three-term recurrence
+// point, and the SM delivers one wavefront per clock against two DFMA warp-instructions -- the one-point kernel runs the
+// shared-memory data pipe at 85 % of its peak with the FP64 pipe at 60 % (profiles/geometry_r01c_ncsx): that pipe, not
+// latency, is its bound (16 warps / SM at 128 registers are 3-9 % slower).  Here a thread owns P = 2 points, so every
+// loaded pair feeds four FMAs, and cos / sin(k nfp phi) are not held as arrays (2 x 28 doubles per point would not fit)
+// but advanced inside the k loop by the three-term recurrence
 //     cos((k+1) x) = 2 cos x cos(k x) - cos((k-1) x)       (+2 FMAs per (m, k) and point on 18: the price of the registers)
 // which also makes the toroidal range a run-time loop bound: one kernel for any |n| / nfp.
+// MEASURED (round 2, B200): halving the wavefronts does not pay -- at 254 registers only 8 warps / SM are resident and the
+// rolled k loop exposes the load latency: NCSX config 3.51 ms (k loop unrolled by 2: 3.30) against 2.95 for the one-point
+// kernel, HBERG 110 / 103 against 92 ms.  It therefore only serves toroidal ranges the templated kernels do not cover
+// (|n| / nfp > 18) and IBS_GEO3D=1.
 #ifndef IBS_GEO3_UNROLL
 #define IBS_GEO3_UNROLL 1
 #endif
@@ -826,17 +831,16 @@ int geometry_dispatch(const double* tab_mn, const double* tab_nyq, const double*
         IBS_REQUIRE(m2[k] >= 0 && std::fabs(xm_nyq[k] - m2[k]) < 1e-9 && std::fabs(xn_nyq[k] - (double)n2[k] * nfp) < 1e-9, "non-integer mode numbers");
         nt2 = std::max(nt2, std::abs(n2[k]));
     }
-    // 3-D tables: the two-points-per-thread kernel takes the toroidal ranges as run-time loop bounds (any |n| / nfp that fits
-    // in shared memory); IBS_GEO3D=0 selects round 1's one-point-per-thread instantiations (|n| / nfp <= 18) for comparison
-    bool use3d = (nt1 > 0 || nt2 > 0);
-    if (const char* e = std::getenv("IBS_GEO3D")) { if (std::atoi(e) == 0) use3d = false; }
+    // 3-D tables: the one-point-per-thread instantiations (|n| / nfp <= 18) are the default; the two-points-per-thread kernel
+    // takes the toroidal ranges as run-time loop bounds, so it serves any wider range (and IBS_GEO3D=1 forces it, for comparison)
+    bool use3d = (nt1 > 16 || nt2 > 18);
+    if (const char* e = std::getenv("IBS_GEO3D")) { if (std::atoi(e) != 0 && (nt1 > 0 || nt2 > 0)) use3d = true; }
     int NT1, NT2;
     if (nt1 == 0 && nt2 == 0) { NT1 = 0; NT2 = 0; }
     else if (use3d) { NT1 = std::max(nt1, 1); NT2 = std::max(nt2, 1); }
     else if (nt1 <= 6 && nt2 <= 8) { NT1 = 6; NT2 = 8; }
     else if (nt1 <= 11 && nt2 <= 13) { NT1 = 11; NT2 = 13; }
-    else if (nt1 <= 16 && nt2 <= 18) { NT1 = 16; NT2 = 18; }
-    else { set_error("toroidal mode range |n|/nfp > 18 is not supported by the one-point-per-thread kernels"); return IBS_ERR_UNSUPPORTED; }
+    else { NT1 = 16; NT2 = 18; }
     const int M1 = mmax1 + 1, M2 = mmax2 + 1, W1 = 2 * NT1 + 1, W2 = 2 * NT2 + 1;
     if (NT1 > 0 && M1 > MAX_M_NEWTON) { set_error("mpol too large for a 3-D equilibrium"); return IBS_ERR_UNSUPPORTED; }
 
