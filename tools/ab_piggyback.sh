@@ -1,10 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/pytest_r02c.txt
-for v in u2; do for wl in ncsx hberg; do echo "variant $v $wl"; IBS_LIB=$PWD/ideal-ballooning-solver_b200/lib/variants/libibs_$v.so python tools/time_stages.py $wl 1 2>&1 | grep -E "geometry"; done; done 2>&1 | tee gpurun_out/ab_geo_r02c.txt
-python bench.py --steps 50 > gpurun_out/bench_r02_d3d.json 2> gpurun_out/bench_r02_d3d.err
-IBS_GEO3D=0 python bench.py --workload ncsx --steps 30 > gpurun_out/bench_r02_ncsx.json 2> gpurun_out/bench_r02_ncsx.err
-IBS_GEO3D=0 python bench.py --workload hberg --steps 10 > gpurun_out/bench_r02_hberg.json 2> gpurun_out/bench_r02_hberg.err
-python bench.py --workload salpha --steps 30 > gpurun_out/bench_r02_salpha.json 2> gpurun_out/bench_r02_salpha.err
-IBS_GEO3D=0 python bench.py --workload adjoint --steps 5 --points 32768 > gpurun_out/bench_r02_adjoint32k.json 2> gpurun_out/bench_r02_adjoint32k.err
-tail -2 gpurun_out/bench_r02_*.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/pytest_r02d.txt
+python tools/time_stages.py d3d 37 2>&1 | tee gpurun_out/time_stages_r02d.txt
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-single > gpurun_out/r2d_plain.json 2> gpurun_out/r2d_plain.err && ncu --set full --clock-control none --import-source on -k regex:scan_solve -s 3 -c 1 -o gpurun_out/prof_scan_r02b python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-single > gpurun_out/r2d_ncu.log 2>&1
+ls -la gpurun_out/prof_scan_r02b.ncu-rep
