@@ -15,6 +15,7 @@
 
 #include "ibs_common.cuh"
 #include "ibs_scan_core.cuh"
+#include "ibs_scan2_core.cuh"
 
 namespace ibs {
 using namespace scan;
@@ -264,6 +265,203 @@ scan_solve_kernel(const ScanParams p) {
     }
 }
 
+// ---- lane-per-chain kernel (ibs_scan2_core.cuh): 16 solves per warp, lane = 16 h + i runs chain h of solve i ---------------
+#ifndef IBS_SCAN2_CTAS
+#define IBS_SCAN2_CTAS 4          // CTAs of 4 warps per SM the kernel is compiled for (register cap 65536 / (128 * CTAS))
+#endif
+constexpr int S2_TILE = scan2::T0 * REC;           // doubles per tile (35 records)
+constexpr int S2_STAGE = 2 * S2_TILE;              // ascending tile (forward lanes) + descending tile (backward lanes)
+constexpr int S2_RING = SC_NSTAGE * S2_STAGE;      // doubles per warp (10 KB with 3 stages)
+
+struct Dev2Ctx {
+    double* ring; uint64_t* bars; unsigned parity; int lane, h;
+    const double* line_base; int N;
+    const double* lvl; int Nl, nst;
+
+    __device__ __forceinline__ void issue(int s) {          // lane 0: both tiles of stage s
+        const int slot = s % SC_NSTAGE;
+        double* dstA = ring + slot * S2_STAGE;
+        double* dstD = dstA + S2_TILE;
+        const int f0 = scan2::stage_first(s), len = scan2::stage_len(s, Nl);
+        mbar_expect_tx(&bars[slot], (unsigned)(2 * len * REC * sizeof(double)));
+        tma_bulk_g2s(dstA, lvl + (size_t)f0 * REC, (unsigned)(len * REC * sizeof(double)), &bars[slot]);
+        tma_bulk_g2s(dstD, lvl + (size_t)(Nl - f0 - len) * REC, (unsigned)(len * REC * sizeof(double)), &bars[slot]);
+    }
+    __device__ __forceinline__ void begin_pass(int lev, int Nl_, int q_max) {
+        lvl = line_base + (size_t)level_offset(N, lev) * REC;
+        Nl = Nl_; nst = scan2::stage_of(q_max + 2) + 1;
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const int n0 = nst < SC_NSTAGE ? nst : SC_NSTAGE;
+            for (int s = 0; s < n0; ++s) issue(s);
+        }
+    }
+    __device__ __forceinline__ void wait(int s) {
+        const int slot = s % SC_NSTAGE;
+        const unsigned addr = (unsigned)__cvta_generic_to_shared(&bars[slot]), par = (parity >> slot) & 1u;
+        unsigned done = 0, spins = 0;
+        while (!done) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(done) : "r"(addr), "r"(par) : "memory");
+            if (!done && ++spins > (1u << 24)) __trap();        // a pipeline bug must trap, not hang the device
+        }
+        parity ^= 1u << slot;
+    }
+    // my record of step q inside stage s: ascending tile for the forward chain, descending tile read backwards for the mirrored one
+    __device__ __forceinline__ const double* ptr(int s, int q) const {
+        const double* t = ring + (s % SC_NSTAGE) * S2_STAGE;
+        const int i = q - scan2::stage_first(s);
+        return h ? t + S2_TILE + (scan2::stage_len(s, Nl) - 1 - i) * REC : t + i * REC;
+    }
+    __device__ __forceinline__ int dstep() const { return h ? -REC : REC; }
+    __device__ __forceinline__ void release(int s) {
+        __syncwarp();
+        if (lane == 0 && s + SC_NSTAGE < nst) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(s + SC_NSTAGE);
+        }
+    }
+    __device__ __forceinline__ double xd(double v) const { return __shfl_xor_sync(FULL, v, 16); }
+    __device__ __forceinline__ int xi(int v) const { return __shfl_xor_sync(FULL, v, 16); }
+    __device__ __forceinline__ Rec rec_k(int k) const {        // record of the matching row (global memory; L2)
+        const double2* q = reinterpret_cast<const double2*>(lvl + (size_t)k * REC);
+        const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+        Rec r; r.G0 = a.x; r.G1 = a.y; r.G2 = b.x; r.C0 = b.y; r.C1 = c.x; r.R = c.y;
+        return r;
+    }
+    // ---- the passes of solve_item2: my chain, the partner's end state by shuffle, the join
+    __device__ __forceinline__ void eval(int lev, int Nl_, int k, double th0, double lam, double& r, double& S, int& nodes) {
+        const int qf = k, qb = Nl_ - 1 - k;
+        const scan2::EvalEnd me = scan2::eval_lane(*this, lev, Nl_, h ? qb : qf, qf > qb ? qf : qb, th0, lam);
+        scan2::EvalEnd ot;
+        ot.X = xd(me.X); ot.W = xd(me.W); ot.S = xd(me.S); ot.nodes = xi(me.nodes);
+        scan2::eval_join(h ? ot : me, h ? me : ot, rec_k(k), th0, lam, r, S, nodes);
+    }
+    __device__ __forceinline__ void out1(int lev, int Nl_, int k, double th0, double lam, SolveOut& out) {
+        const int qf = k, qb = Nl_ - 1 - k;
+        const Sweep me = scan2::out_lane<false>(*this, lev, Nl_, h ? qb : qf, qf > qb ? qf : qb, h != 0, th0, lam, 0.0, 0, nullptr);
+        Sweep ot;
+        ot.x = xd(me.x); ot.E = xi(me.E); ot.W2 = xd(me.W2); ot.W3 = xd(me.W3); ot.W4 = xd(me.W4); ot.gp = xd(me.gp); ot.gpp = xd(me.gpp);
+        ot.a0e = xd(me.a0e); ot.a0o = xd(me.a0o); ot.a1e = xd(me.a1e); ot.a1o = xd(me.a1o); ot.aDe = xd(me.aDe); ot.aDo = xd(me.aDo);
+        ot.aEnd = xd(me.aEnd); ot.vmax = xd(me.vmax); ot.jmax = xi(me.jmax); ot.bad = xi((int)me.bad) != 0;
+        scan2::out_join(h ? ot : me, h ? me : ot, rec_k(k), th0, lam, k, out);
+    }
+    __device__ __forceinline__ void out2(int lev, int Nl_, int k, double th0, double lam, const SolveOut& out, double* Xw) {
+        const int qf = k, qb = Nl_ - 1 - k;
+        const bool ok = !out.bad && out.zmax > 0.0 && out.zmax < 1e300;
+        const double xk = h ? out.xkb : out.xkf;
+        scan2::out_lane<true>(*this, lev, Nl_, h ? qb : qf, qf > qb ? qf : qb, h != 0, th0, lam, ok ? NORM_INFLATE / (xk * out.zmax) : 0.0,
+                              -(h ? out.Ekb : out.Ekf), Xw);
+    }
+    __device__ __forceinline__ bool all(bool b) const { return __all_sync(FULL, b); }
+    __device__ __forceinline__ bool any(bool b) const { return __any_sync(FULL, b); }
+    __device__ __forceinline__ int min_i(int v) const { return __reduce_min_sync(FULL, v); }
+    __device__ __forceinline__ int max_i(int v) const { return __reduce_max_sync(FULL, v); }
+    __device__ __forceinline__ int first_i(int v) const {
+        const unsigned m = __ballot_sync(FULL, v >= 0);
+        return __shfl_sync(FULL, v, m ? (__ffs(m) - 1) : 0);
+    }
+    __device__ __forceinline__ void sync_mem() const { __syncwarp(); }
+    __device__ __forceinline__ double ld(const double* p) const { return __ldcg(p); }
+    // zero-fill invalid solves / form dX: one solve at a time (the forward lane of each flagged pair), rows dealt out over 32 lanes
+    __device__ __forceinline__ void fixup(bool flag, double* Xrow, double* dXrow, int N_, bool bad, double hh, bool want_dX) {
+        __syncwarp();
+        unsigned m = __ballot_sync(FULL, flag) & 0xffffu;
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const bool bd = __shfl_sync(FULL, (int)bad, l) != 0;
+            double* X = reinterpret_cast<double*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(Xrow), l));
+            double* dX = reinterpret_cast<double*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(dXrow), l));
+            fixup_solve(*this, X, want_dX ? dX : nullptr, N_, bd, hh, lane, 32);
+        }
+        __syncwarp();
+    }
+};
+
+__global__ void __launch_bounds__(SC_WARPS * 32, IBS_SCAN2_CTAS)
+scan2_solve_kernel(const ScanParams p) {
+    extern __shared__ __align__(128) double sc_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, li = lane & 15;
+    Dev2Ctx ctx;
+    ctx.ring = sc_smem + warp * S2_RING;
+    ctx.bars = reinterpret_cast<uint64_t*>(sc_smem + SC_WARPS * S2_RING) + warp * SC_NSTAGE;
+    // one block of cold state per PAIR of lanes (both run the same bookkeeping and store the same values)
+    ColdState<1>& cold = *reinterpret_cast<ColdState<1>*>(sc_smem + SC_WARPS * S2_RING + SC_WARPS * SC_NSTAGE +
+                                                          (size_t)(warp * scan2::NH + li) * ColdStride<1>::value);
+    ctx.parity = 0; ctx.lane = lane; ctx.h = h; ctx.N = p.N;
+    if (lane == 0) {
+        for (int s = 0; s < SC_NSTAGE; ++s) mbar_init(&ctx.bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int N = p.N;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(p.counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= p.nitems) break;
+        const int line = item / p.groups, grp = item - line * p.groups;
+        const int idx = grp * scan2::NH + li;
+        const bool act = idx < p.nth0;
+        const size_t sidx = (size_t)line * p.nth0 + (act ? idx : p.nth0 - 1);
+        const double th0 = p.theta0[sidx];
+        const double sg = p.sigma ? p.sigma[sidx] : 0.0;
+        double* Xrow = (act && p.X_rows) ? p.X_rows + sidx * N : nullptr;
+        double* dXrow = (act && p.dX_out) ? p.dX_out + sidx * N : nullptr;
+        ItemProblem P;
+        P.N = N; P.nlev = p.nlev; P.h = p.h; P.U = p.bounds[2 * line]; P.Lb = p.bounds[2 * line + 1];
+        P.want_X = p.X_rows != nullptr; P.want_dX = p.dX_out != nullptr;
+        ctx.line_base = p.poly + (size_t)line * p.rows_total * REC;
+        ItemResult res;
+        scan2::solve_item2(ctx, P, th0, act, sg, p.sigma != nullptr, Xrow, dXrow, res, cold);
+        if (act && h == 0) {
+            p.lam_out[sidx] = res.gam;
+            if (p.lam_matrix_out) p.lam_matrix_out[sidx] = res.rho;
+            if (p.info_out) p.info_out[sidx] = res.info;
+        }
+        if (p.items_per_surface > 0) {
+            // ---- fused arg-max (see scan_solve_kernel): the forward lanes carry the solves
+            const int surf = line / p.lines_per_surface;
+            double bv = -INFINITY; int bi = 0x7fffffff, anynan = 0;
+            if (act && h == 0) {
+                const double v = res.gam;
+                if (v != v) anynan = 1;
+                best_merge(bv, bi, v, (line - surf * p.lines_per_surface) * p.nth0 + idx);
+            }
+            warp_best(bv, bi, anynan);
+            unsigned prev = 0;
+            if (lane == 0) {
+                p.item_val[item] = bv;
+                p.item_idx[item] = anynan ? -2 : bi;
+                __threadfence();
+                prev = atomicAdd(&p.surf_count[surf], 1u);
+            }
+            prev = __shfl_sync(FULL, prev, 0);
+            if (prev == (unsigned)p.items_per_surface - 1u) {
+                __threadfence();
+                bv = -INFINITY; bi = 0x7fffffff; anynan = 0;
+                const int i0 = surf * p.items_per_surface;
+                for (int i = lane; i < p.items_per_surface; i += 32) {
+                    const double v = __ldcg(p.item_val + i0 + i);
+                    const int k = __ldcg(p.item_idx + i0 + i);
+                    if (k == -2) anynan = 1; else best_merge(bv, bi, v, k);
+                }
+                warp_best(bv, bi, anynan);
+                if (lane == 0) {
+                    double val, idxd, sgm;
+                    if (anynan) { val = __longlong_as_double(0x7ff8000000000000LL); idxd = -2.0; sgm = 0.05; }
+                    else if (bv == 0.0) { val = bv; idxd = -1.0; sgm = 0.05; }
+                    else { val = bv; idxd = (double)bi; sgm = __dadd_rn(__dmul_rn(1.3, fabs(bv)), 0.05); }
+                    p.best_out[2 * surf] = val; p.best_out[2 * surf + 1] = idxd;
+                    if (p.sigma0_out) p.sigma0_out[surf] = sgm;
+                }
+            }
+        }
+    }
+}
+
 // ---- preparation: one CTA per field line ----------------------------------------------------------------
 constexpr int PREP_T = 256;
 
@@ -376,13 +574,44 @@ static int scan_launch(const ScanParams& sp, cudaStream_t stream) {
     return IBS_OK;
 }
 
+static size_t scan2_smem_bytes() {
+    return (size_t)SC_WARPS * S2_RING * sizeof(double) + (size_t)SC_WARPS * SC_NSTAGE * sizeof(uint64_t) +
+           (size_t)SC_WARPS * scan2::NH * ColdStride<1>::value * sizeof(double);
+}
+static int scan2_launch(const ScanParams& sp, cudaStream_t stream) {
+    const size_t smem = scan2_smem_bytes();
+    static bool configured[IBS_MAX_DEVICES] = {false};
+    const int dslot = current_device_slot();
+    if (!configured[dslot]) {
+        IBS_CUDA_CHECK(cudaFuncSetAttribute(scan2_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IBS_CUDA_CHECK(cudaFuncSetAttribute(scan2_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured[dslot] = true;
+    }
+    int per_sm = 0;
+    IBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan2_solve_kernel, SC_WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (const char* e = std::getenv("IBS_MAX_CTAS_PER_SM")) { const int v = std::atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
+    const long long cap = (long long)num_sms() * per_sm;
+    const long long need = ((long long)sp.nitems + SC_WARPS - 1) / SC_WARPS;
+    const int grid = (int)(need < cap ? need : cap);
+    scan2_solve_kernel<<<grid, SC_WARPS * 32, smem, stream>>>(sp);
+    IBS_CUDA_CHECK(cudaGetLastError());
+    return IBS_OK;
+}
+// which of the two lane kernels a batch of N-point lines goes to (IBS_SCAN2=0: always the two-chains-per-lane kernel)
+static bool use_scan2(int N) {
+    if (const char* e = std::getenv("IBS_SCAN2")) { if (std::atoi(e) == 0) return false; }
+    return scan2::scan2_size_ok(N);
+}
+
 // One launch set (prep + solver) for the lines [l0, l0 + nline) of the batch p
 static int scan_solve_lines(const SolveParams& p, int l0, int nline, int spl, bool two, cudaStream_t stream) {
     const int N = p.N;
     const int nlev = num_levels(N);
     const int rows_total = level_offset(N, nlev + 1);
     const size_t v0 = (size_t)l0 * p.nth0, nsolve = (size_t)nline * p.nth0;
-    const int groups = (p.nth0 + 32 * spl - 1) / (32 * spl);
+    const bool s2 = !two && spl == 1 && use_scan2(N);
+    const int groups = s2 ? (p.nth0 + scan2::NH - 1) / scan2::NH : (p.nth0 + 32 * spl - 1) / (32 * spl);
     const int nitems = nline * groups;
     const bool fused = p.lines_per_surface > 0 && p.best_out;
     const int nsurf = fused ? nline / p.lines_per_surface : 0;
@@ -428,7 +657,9 @@ static int scan_solve_lines(const SolveParams& p, int l0, int nline, int spl, bo
                                                        rows_total, (double*)(ws + o_poly), (double*)(ws + o_bounds));
         if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) rc = cuda_fail(e, "scan_prep_kernel launch");
     }
-    if (rc == IBS_OK) {
+    if (rc == IBS_OK && s2) {
+        rc = scan2_launch(sp, stream);
+    } else if (rc == IBS_OK) {
         if (two && spl == 1) {
             rc = scan_launch<1, MODE_ITER>(sp, stream);
             if (rc == IBS_OK) { ScanParams sp2 = sp; sp2.counter = sp.counter + 1; rc = scan_launch<1, MODE_OUT>(sp2, stream); }

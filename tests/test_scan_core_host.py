@@ -102,3 +102,42 @@ def test_lane_code_small_grids(harness, n):
         X = X * np.sign(X[np.argmax(np.abs(X))])
         assert abs(R["lam"][0, t] - gam) <= LAM_RTOL * abs(gam)
         np.testing.assert_allclose(R["X"][t], X, rtol=0, atol=X_ATOL)
+
+
+def test_lane_per_chain_code_matches_oracle_and_two_chain_code(harness):
+    """The lane code of scan2_solve_kernel (one chain per lane, mirrored backward chain, chains joined at a row that is a
+    multiple of 16) on D3D- and NCSX-like lines of the bench's synthetic equilibria: against the oracle (LAPACK route) and
+    against the two-chains-per-lane code (same pencil, same shift sequence -> agreement to rounding)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    import bench
+    from oracle import ballooning_oracle as bo
+    shc, lib = harness
+    for wl, alpha0, N in (("d3d", 0.0, 1025), ("ncsx", 0.7, 513)):
+        st, _, _, _ = bench.build_tables(wl, 1, 0)
+        theta = np.linspace(-4 * np.pi, 4 * np.pi, N)
+        assert lib.scan2_host_size_ok(N)
+        rng = np.random.default_rng(1)
+        lines = rng.choice(st.ns, 3, replace=False)
+        base, dP = [], []
+        for js in lines:
+            fl = bo.fieldlines(st.select([js]), np.array([alpha0]), theta)
+            base.append(np.stack([getattr(fl, n)[0][0] for n in shc.BASE_NAMES])); dP.append(bo.dpdrho_of(fl))
+        base, dP = np.stack(base), np.array(dP)
+        th0 = np.tile(np.array([0.0, 0.6, 1.3]), (len(lines), 1))
+        h = theta[1] - theta[0]
+        A = shc.host_scan_solve(lib, base, dP, th0, h, kernel="scan")
+        B = shc.host_scan_solve(lib, base, dP, th0, h, kernel="scan2")
+        assert np.all((B["info"] >> 16) == 0)
+        np.testing.assert_allclose(B["lam"], A["lam"], rtol=1e-12)
+        np.testing.assert_allclose(B["X"], A["X"], rtol=0, atol=1e-10)
+        for li in range(len(lines)):
+            for t in range(th0.shape[1]):
+                cv = base[li][2] + th0[li, t] * base[li][3]
+                gd = base[li][4] + 2 * th0[li, t] * base[li][5] + th0[li, t] ** 2 * base[li][6]
+                gam, X, dX, *_ = bo.gamma_ball_full(dP[li], theta, base[li][0], base[li][1], cv, gd, method="lambda_max")
+                sg = np.sign(X[np.argmax(np.abs(X))])
+                s = li * th0.shape[1] + t
+                assert abs(B["lam"][li, t] - gam) <= LAM_RTOL * abs(gam)
+                np.testing.assert_allclose(B["X"][s], X * sg, rtol=0, atol=X_ATOL)
+                np.testing.assert_allclose(B["dX"][s], dX * sg, rtol=0, atol=10 * X_ATOL * max(1.0, np.max(np.abs(dX))))
+    assert not lib.scan2_host_size_ok(969) and not lib.scan2_host_size_ok(1024)

@@ -18,12 +18,14 @@ BASE_NAMES = ["bmag", "gradpar_theta_pest", "cvdrift", "cvdrift0", "gds2", "gds2
 
 
 def build(outdir="/tmp/sch"):
+    """Compile the harness (tools/scan2_core_host.cpp: it includes scan_core_host.cpp, so one library carries the lane code
+    of both kernels: scan_host_solve = two chains per lane, scan2_host_solve = one chain per lane)."""
     os.makedirs(outdir, exist_ok=True)
     so = os.path.join(outdir, "scan_core_host.so")
-    src = os.path.join(ROOT, "tools", "scan_core_host.cpp")
-    hdr = os.path.join(ROOT, "ideal-ballooning-solver_b200", "csrc", "ibs_scan_core.cuh")
-    if not os.path.isfile(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so, src])
+    srcs = [os.path.join(ROOT, "tools", n) for n in ("scan2_core_host.cpp", "scan_core_host.cpp")]
+    hdrs = [os.path.join(ROOT, "ideal-ballooning-solver_b200", "csrc", n) for n in ("ibs_scan_core.cuh", "ibs_scan2_core.cuh")]
+    if not os.path.isfile(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs + hdrs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so, srcs[0]])
     lib = ctypes.CDLL(so)
     dp = ctypes.POINTER(ctypes.c_double)
     ip = ctypes.POINTER(ctypes.c_int)
@@ -33,6 +35,9 @@ def build(outdir="/tmp/sch"):
     lib.scan_host_solve.restype = ctypes.c_long
     lib.scan_host_last_cost.restype = ctypes.c_double
     lib.scan_host_solve.argtypes = [dp, dp, dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, dp, dp, dp, ip]
+    lib.scan2_host_solve.restype = ctypes.c_long
+    lib.scan2_host_solve.argtypes = lib.scan_host_solve.argtypes
+    lib.scan2_host_size_ok.restype = ctypes.c_int
     if os.environ.get("IBS_SCAN_TWO"):
         lib.scan_host_set_two_kernel(int(os.environ["IBS_SCAN_TWO"]))
     return lib
@@ -42,8 +47,9 @@ def _p(a, t=ctypes.c_double):
     return a.ctypes.data_as(ctypes.POINTER(t)) if a is not None else None
 
 
-def host_scan_solve(lib, base, dPdrho, theta0, h, sigma=None, want_X=True, want_dX=True):
-    """base (nline, 8, N), dPdrho (nline,), theta0 (nline, nth0) -> dict of results from the CPU harness."""
+def host_scan_solve(lib, base, dPdrho, theta0, h, sigma=None, want_X=True, want_dX=True, kernel="scan"):
+    """base (nline, 8, N), dPdrho (nline,), theta0 (nline, nth0) -> dict of results from the CPU harness.
+    kernel = "scan": lane code of scan_solve_kernel (two chains per lane); "scan2": of scan2_solve_kernel (one chain per lane)."""
     base = np.ascontiguousarray(base, dtype=np.float64)
     nline, _, N = base.shape
     theta0 = np.ascontiguousarray(theta0, dtype=np.float64)
@@ -59,7 +65,7 @@ def host_scan_solve(lib, base, dPdrho, theta0, h, sigma=None, want_X=True, want_
     dX = np.full((n, N), np.nan) if want_dX else None
     info = np.zeros(n, dtype=np.int32)
     sg = np.ascontiguousarray(sigma, dtype=np.float64) if sigma is not None else None
-    passes = lib.scan_host_solve(_p(poly), _p(bounds), _p(theta0), _p(sg), nline, nth0, N, float(h), _p(lam), _p(lm), _p(X), _p(dX),
+    passes = (lib.scan2_host_solve if kernel == "scan2" else lib.scan_host_solve)(_p(poly), _p(bounds), _p(theta0), _p(sg), nline, nth0, N, float(h), _p(lam), _p(lm), _p(X), _p(dX),
                                  _p(info, ctypes.c_int))
     return dict(lam=lam.reshape(nline, nth0), lam_matrix=lm.reshape(nline, nth0), X=X, dX=dX, info=info.reshape(nline, nth0),
                 passes=passes, bounds=bounds, poly=poly, cost=lib.scan_host_last_cost())
