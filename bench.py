@@ -62,8 +62,18 @@ def scan_eligible(nth0, N):
     return os.environ.get("IBS_SCAN", "1") != "0" and nth0 >= 4 and (N & 1) == 1 and N >= 65
 
 
+def scan2_size_ok(N):
+    """Mirrors scan2_size_ok (ibs_scan2_core.cuh): the lane-per-chain kernel needs N - 1 (and the coarsest level's) to be a multiple of 16."""
+    nlev = 0
+    while nlev < 4 and (N - 1) % (2 << nlev) == 0 and ((N - 1) >> (nlev + 1)) + 1 >= 65:
+        nlev += 1
+    return N % 2 == 1 and N >= 65 and (N - 1) % 16 == 0 and ((N - 1) >> nlev) % 16 == 0 and os.environ.get("IBS_SCAN2", "1") != "0"
+
+
 def solver_kernel_name(nth0, N):
-    return "scan_solve_kernel (K2+K3, lane per solve)" if scan_eligible(nth0, N) else "solve_kernel (K2+K3, team per solve)"
+    if not scan_eligible(nth0, N):
+        return "solve_kernel (K2+K3, team per solve)"
+    return "scan2_solve_kernel (K2+K3, lane per chain)" if scan2_size_ok(N) else "scan_solve_kernel (K2+K3, lane per solve)"
 
 
 def workload_grids(name):
