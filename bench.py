@@ -99,7 +99,8 @@ def build_tables(name, equilibria, seed0):
     parts = [tables.RadialSplines(synthetic.make_equilibrium(kind, seed=seed0 + e)).evaluate(s) for e in range(equilibria)]
     st = dataclasses.replace(parts[0], tab_mn=np.concatenate([p.tab_mn for p in parts]),
                              tab_nyq=np.concatenate([p.tab_nyq for p in parts]),
-                             scal=np.concatenate([p.scal for p in parts]))
+                             scal=np.concatenate([p.scal for p in parts]),
+                             bsupumnc=None if parts[0].bsupumnc is None else np.concatenate([p.bsupumnc for p in parts]))
     return st, alpha, theta0, theta
 
 
@@ -115,6 +116,28 @@ def describe(workload, equilibria=1, points=None, strong=False):
     how = "ONE batch sharded over the ranks by surface blocks" if strong else "per step per GPU"
     return (f"{kind.upper()}-like synthetic VMEC-shaped scan: {ns} surfaces x {na} alpha x {nt} theta0, ntheta={nth} "
             f"(N={nth + 1} points, theta in +-{span}pi), x {equilibria} equilibria {how}")
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Everything a library prints on fd 1 (NCCL's version banner under NCCL_DEBUG=VERSION/WARN, ...) goes to stderr from here
+    on; ``emit`` writes the ONE JSON line on the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 def load_peaks():
@@ -351,7 +374,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": kind_cpu, "sample": sample},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -424,7 +447,7 @@ class Harness:
 
     def finish(self, line):
         if self.rank == 0 and line is not None:
-            print(json.dumps(line), flush=True)
+            emit(line)
         if self.world > 1:
             self.dist.destroy_process_group()
 
@@ -790,6 +813,7 @@ def run_adjoint(H, args):
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

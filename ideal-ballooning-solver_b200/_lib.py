@@ -27,6 +27,8 @@ SIGNATURES = {
     "ibs_geometry_full_nfields": (c_int, []),
     "ibs_geometry_full": (c_int, [_D, _D, _D, _D, _D, _D, _D, _D, c_int, c_int, c_int, c_double, c_double, _D, c_int, _D, c_int,
                                   c_int, c_double, c_int, c_double, _D, _I, c_void_p]),
+    "ibs_geometry_adjoint": (c_int, [_D, _D, _D, _D, _D, _D, _D, c_int, c_int, c_int, c_double, c_double, _D, _D, c_int, c_double,
+                                     _D, _D, _D, _D, _D, _D, _D, _D, c_void_p]),
     "ibs_solve_gcf_batch": (c_int, [_D, _D, _D, c_int, c_int, c_double, _D, _D, c_int, _D, _D, _D, _D, _I, c_void_p]),
     "ibs_solve_base_batch": (c_int, [_D, _D, _D, _I, c_int, c_int, c_int, c_double, _D, _D, c_int,
                                      _D, _D, _D, _D, _D, _D, _D, _I, c_void_p]),

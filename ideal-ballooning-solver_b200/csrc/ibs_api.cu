@@ -29,6 +29,11 @@ int launch_centre_lines(int* line, int n, cudaStream_t st);
 int launch_argmax(const double* gamma, int ns, int ngrid, double* val, int* idx, double* sigma0, cudaStream_t st);
 int launch_argmax_packed(const double* gamma, int ns, int ngrid, double* best, double* sigma0, cudaStream_t st);
 bool scan_solver_eligible(const SolveParams& p);
+int geometry_adjoint_dispatch(const double* tab_mn, const double* tab_nyq, const double* scal, const double* xm, const double* xn,
+                              const double* xm_nyq, const double* xn_nyq, int ns, int mnmax, int mnmax_nyq, double phiedge,
+                              double aminor_p, const double* alpha, const double* theta, int nl, double phi_center,
+                              const double* theta0, const double* dPdrho, const double* sg, const double* sc, const double* sf,
+                              const double* Q, double* grad_mn, double* grad_nyq, cudaStream_t st);
 int geometry_full_nfields();
 int geometry_full_dispatch(const double* tab_mn, const double* tab_nyq, const double* bsupumnc, const double* scal,
                            const double* xm, const double* xn, const double* xm_nyq, const double* xn_nyq,
@@ -201,6 +206,22 @@ int ibs_geometry_full(const double* tab_mn, const double* tab_nyq, const double*
     return geometry_full_dispatch(tab_mn, tab_nyq, bsupumnc, scal, xm, xn, xm_nyq, xn_nyq, ns, mnmax, mnmax_nyq, phiedge, aminor_p,
                                   alpha, nalpha, grid, nl, mode, theta_shift, zero_xn_nyq, phi_center, out, info_out,
                                   (cudaStream_t)stream);
+}
+
+int ibs_geometry_adjoint(const double* tab_mn, const double* tab_nyq, const double* scal,
+                         const double* xm, const double* xn, const double* xm_nyq, const double* xn_nyq,
+                         int ns, int mnmax, int mnmax_nyq, double phiedge, double aminor_p,
+                         const double* alpha, const double* theta, int nl, double phi_center,
+                         const double* theta0, const double* dPdrho, const double* dlam_dg, const double* dlam_dc,
+                         const double* dlam_df, const double* Q, double* grad_mn_out, double* grad_nyq_out, void* stream) {
+    IBS_REQUIRE(ns >= 0 && nl >= 1 && mnmax >= 1 && mnmax_nyq >= 1, "bad sizes");
+    if (ns == 0) return IBS_OK;
+    IBS_REQUIRE(tab_mn && tab_nyq && scal && xm && xn && xm_nyq && xn_nyq && alpha && theta && theta0 && dPdrho && dlam_dg && dlam_dc &&
+                dlam_df && Q && grad_mn_out && grad_nyq_out, "null pointer");
+    IBS_REQUIRE(aminor_p > 0.0 && phiedge != 0.0, "Aminor_p must be > 0 and phiedge != 0");
+    return geometry_adjoint_dispatch(tab_mn, tab_nyq, scal, xm, xn, xm_nyq, xn_nyq, ns, mnmax, mnmax_nyq, phiedge, aminor_p, alpha, theta,
+                                     nl, phi_center, theta0, dPdrho, dlam_dg, dlam_dc, dlam_df, Q, grad_mn_out, grad_nyq_out,
+                                     (cudaStream_t)stream);
 }
 
 int ibs_solve_gcf_batch(const double* g, const double* c, const double* f, int nsolve, int N, double h,

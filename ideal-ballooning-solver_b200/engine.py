@@ -304,6 +304,29 @@ def adjoint_sensitivities(lam, X, dX, f):
     return tuple(outs)
 
 
+def geometry_adjoint(tables: DeviceTables, alpha, theta, theta0, dPdrho, dlam_dg, dlam_dc, dlam_df, Q, phi_center: float = 0.0):
+    """Reverse mode of K1 (``ibs_geometry_adjoint``): ``d lambda / d tab_mn (ns, 6, mnmax)`` and ``d lambda / d tab_nyq
+    (ns, 7, mnmax_nyq)`` for one field line per surface, from the per-point Hellmann-Feynman sensitivities."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    dev = tables.tab_mn.device
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    f = lambda t, nm: _f64(t, dev, nm)
+    alpha, theta, theta0, dP = f(alpha, "alpha").reshape(-1), f(theta, "theta").reshape(-1), f(theta0, "theta0").reshape(-1), f(dPdrho, "dPdrho").reshape(-1)
+    ns, nl = tables.ns, theta.numel()
+    sg, sc, sf, Q = f(dlam_dg, "dlam_dg").reshape(ns, nl), f(dlam_dc, "dlam_dc").reshape(ns, nl), f(dlam_df, "dlam_df").reshape(ns, nl), f(Q, "Q").reshape(ns)
+    xm, xn, xmq, xnq = up(tables.xm), up(tables.xn), up(tables.xm_nyq), up(tables.xn_nyq)
+    gmn = torch.empty_like(tables.tab_mn)
+    gnq = torch.empty_like(tables.tab_nyq)
+    with torch.cuda.device(dev):
+        rc = lib.ibs_geometry_adjoint(_ptr(tables.tab_mn), _ptr(tables.tab_nyq), _ptr(tables.scal), _ptr(xm), _ptr(xn), _ptr(xmq), _ptr(xnq),
+                                      ns, xm.numel(), xmq.numel(), tables.phiedge, tables.Aminor_p, _ptr(alpha), _ptr(theta), nl,
+                                      float(phi_center), _ptr(theta0), _ptr(dP), _ptr(sg), _ptr(sc), _ptr(sf), _ptr(Q), _ptr(gmn), _ptr(gnq),
+                                      _stream())
+    _lib.check(rc, "ibs_geometry_adjoint")
+    return gmn, gnq
+
+
 def obj_w_grad_batch(base3, dPdrho3, theta0, h: float, del_alpha: float = 0.004, lam0=None, want_X=False):
     """Batched ``obj_w_grad`` (``utils.py:1632-1728``): ``base3`` is ``(npoint, 3, 8, N)`` holding the
     lines ``alpha - del/2, alpha, alpha + del/2``.  Returns ``(val, grad, X, dX, info)`` with

@@ -420,6 +420,41 @@ def hellmann_feynman_gamma(tables0: engine.DeviceTables, tables_pert, alpha_star
     return GammaSensitivity(sol.lam.cpu().numpy(), grad.t().contiguous().cpu().numpy(), sol.X.cpu().numpy())
 
 
+@dataclasses.dataclass
+class TableGradient:
+    gamma: np.ndarray          # (ns,) growth rate at (alpha*, theta0*)
+    grad_mn: torch.Tensor      # (ns, 6, mnmax)      d gamma / d tab_mn
+    grad_nyq: torch.Tensor     # (ns, 7, mnmax_nyq)  d gamma / d tab_nyq
+
+    def predict(self, tables0: engine.DeviceTables, tables_pert) -> np.ndarray:
+        """First-order change of every surface's growth rate for each perturbed table set: ``(ndof, ns)``."""
+        out = []
+        for tp in tables_pert:
+            d = ((tp.tab_mn - tables0.tab_mn) * self.grad_mn).sum(dim=(1, 2)) + ((tp.tab_nyq - tables0.tab_nyq) * self.grad_nyq).sum(dim=(1, 2))
+            out.append(d.cpu().numpy())
+        return np.array(out).reshape(len(out), -1)
+
+
+def table_gradient(tables0: engine.DeviceTables, alpha_star, theta0_star, theta) -> TableGradient:
+    """the gradient of every surface's maximum growth rate with respect to EVERY Fourier table
+    coefficient of its surface, from one eigen-solve per surface -- reverse mode through K1 (``ibs_geometry_adjoint``): K1 on
+    the arg-max line -> K2/K3 -> per-point Hellmann-Feynman sensitivities (K4, ``utils.py:1676-1680``) -> adjoint of the
+    geometry.  The ``ndofs`` perturbed-equilibrium scans of ``sims_runner_NCSX.py:245-262`` become ``ndofs`` dot products
+    (``TableGradient.predict``); ``hellmann_feynman_gamma`` (one K1 per DOF) is the finite-perturbation form of the same."""
+    dev = tables0.tab_mn.device
+    theta_np = theta.cpu().numpy() if isinstance(theta, torch.Tensor) else np.asarray(theta, dtype=np.float64)
+    h = engine.grid_spacing(theta_np)
+    a = torch.as_tensor(np.asarray(alpha_star, dtype=np.float64)).reshape(-1, 1).to(dev)
+    t0 = torch.as_tensor(np.asarray(theta0_star, dtype=np.float64)).reshape(-1).to(dev)
+    geo = engine.geometry_batch(tables0, a, theta_np)
+    sol = engine.solve_base_batch(geo.base, geo.dPdrho, t0, h, nth0=1, want_dX=True, want_matrix=False, want_gcf=True)
+    sg, sc, sf = engine.adjoint_sensitivities(sol.lam, sol.X, sol.dX, sol.f)
+    dP = geo.dPdrho.reshape(-1)
+    Q = (sc * sol.c).sum(dim=1) / (-dP)
+    gmn, gnq = engine.geometry_adjoint(tables0, a.reshape(-1), theta_np, t0, dP, sg, sc, sf, Q)
+    return TableGradient(sol.lam.cpu().numpy(), gmn, gnq)
+
+
 def save_results(path: str, dof_idx: int, iter0: int, result: BallScanResult) -> None:
     """Append one row per call to ``ball_gam<dof>.npy``, ``ball_theta0<dof>.npy``, ``ball_alpha<dof>.npy`` with the
     reference's semantics (``ball_scan.py:359-384``): at ``iter0 == 0`` the placeholder first element written by

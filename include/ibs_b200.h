@@ -103,6 +103,21 @@ int ibs_geometry_full(const double* tab_mn, const double* tab_nyq, const double*
                       const double* alpha, int nalpha, const double* grid, int nl, int mode, double theta_shift,
                       int zero_xn_nyq, double phi_center, double* out, int* info_out, void* stream);
 
+/* Reverse mode of K1: d(lambda) / d(Fourier table coefficient) for ns field lines, one per surface (row f3: replaces the
+ * ndofs + 1 perturbed-equilibrium scans of sims_runner_NCSX.py:245-262 by ONE scan + this call + dot products with the
+ * table perturbations).  Chains the Hellmann-Feynman sensitivities of ibs_adjoint_sensitivities (utils.py:1676-1680) through
+ * g, c, f (utils.py:1560-1562), the theta0 shift (ball_scan.py:267-268), dPdrho (ball_scan.py:262), the pointwise geometry
+ * (utils.py:474-720), the theta_vmec root (utils.py:391-416) and the mode sums (utils.py:432-468), at fixed iota(s), p'(s).
+ *   tables / modes as ibs_geometry_full (ALL device pointers); alpha [ns], theta0 [ns], dPdrho [ns]: the line of each surface;
+ *   dlam_dg, dlam_dc, dlam_df [ns][nl]; Q [ns] = sum_j dlam_dc_j c_j / (-dPdrho);
+ *   grad_mn_out [ns][6][mnmax], grad_nyq_out [ns][7][mnmax_nyq]: d lambda / d tab_mn, d lambda / d tab_nyq.              */
+int ibs_geometry_adjoint(const double* tab_mn, const double* tab_nyq, const double* scal,
+                         const double* xm, const double* xn, const double* xm_nyq, const double* xn_nyq,
+                         int ns, int mnmax, int mnmax_nyq, double phiedge, double aminor_p,
+                         const double* alpha, const double* theta, int nl, double phi_center,
+                         const double* theta0, const double* dPdrho, const double* dlam_dg, const double* dlam_dc,
+                         const double* dlam_df, const double* Q, double* grad_mn_out, double* grad_nyq_out, void* stream);
+
 /* ---- K2+K3: discretisation + lambda_max + eigenfunction -------------------------------------------
  * Batched gamma_ball_full (utils.py:1550-1624): g, c, f -> half-grid g, second-order finite
  * differences, Dirichlet ends (utils.py:1564-1592) -> largest eigenvalue and eigenvector of

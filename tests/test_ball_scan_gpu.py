@@ -97,3 +97,58 @@ def test_hellmann_feynman_gamma_predicts_perturbed_growth_rates(cuda_lib):
         np.testing.assert_allclose(sens.dgamma[k], actual, rtol=2e-3, atol=1e-12 * np.abs(sens.gamma).max() + 1e-14)
     f, df = penalty.hf_jacobian([0.3] * 4, sens.gamma, sens.dgamma, np.array([0.0, eps, eps, eps]), thresh=float(np.median(sens.gamma)))
     assert np.all(np.isfinite(df)) and df.shape == (1, 4)
+
+
+def test_table_gradient_reverse_mode_k1(cuda_lib):
+    """f3 proper: d gamma / d (Fourier table coefficient) by reverse mode through K1, against (i) the finite-perturbation
+    Hellmann-Feynman prediction (K1 re-run per perturbed table set) and (ii) actually re-solving the perturbed problems, and
+    (iii) central finite differences of single coefficients."""
+    import dataclasses
+    import torch
+    from ideal_ballooning_solver_b200 import engine, scan, synthetic, tables
+    st = tables.RadialSplines(synthetic.make_equilibrium("ncsx", seed=11)).evaluate(np.linspace(0.55, 0.9, 6))
+    theta = np.linspace(-3 * np.pi, 3 * np.pi, 513)
+    rng = np.random.default_rng(5)
+    a_star, t_star = rng.uniform(0.2, 2.5, st.ns), rng.uniform(0.0, 1.2, st.ns)
+    dt0 = engine.DeviceTables.from_host(st)
+    tg = scan.table_gradient(dt0, a_star, t_star, theta)
+    assert tg.grad_mn.shape == dt0.tab_mn.shape and tg.grad_nyq.shape == dt0.tab_nyq.shape
+    assert bool(torch.isfinite(tg.grad_mn).all()) and bool(torch.isfinite(tg.grad_nyq).all())
+    eps = 1.0e-5
+    perts = []
+    for k in range(3):
+        w_mn = 1.0 + eps * rng.standard_normal(st.tab_mn.shape[1:])[None] * np.exp(-0.3 * np.arange(st.tab_mn.shape[2]))[None, None]
+        w_nq = 1.0 + eps * rng.standard_normal(st.tab_nyq.shape[1:])[None] * np.exp(-0.3 * np.arange(st.tab_nyq.shape[2]))[None, None]
+        perts.append(dataclasses.replace(st, tab_mn=st.tab_mn * w_mn, tab_nyq=st.tab_nyq * w_nq))
+    dts = [engine.DeviceTables.from_host(p) for p in perts]
+    pred = tg.predict(dt0, dts)                                                   # (3, ns) dot products
+    hf = scan.hellmann_feynman_gamma(dt0, dts, a_star, t_star, theta)             # K1 per perturbed set + K4
+    np.testing.assert_allclose(tg.gamma, hf.gamma, rtol=1e-12)
+    # same first-order quantity: the analytic derivative vs a finite perturbation of size eps
+    np.testing.assert_allclose(pred, hf.dgamma, rtol=5e-4, atol=1e-9 * np.abs(hf.dgamma).max())
+    # (ii) against re-solving the perturbed problems (first order in eps)
+    h = engine.grid_spacing(theta)
+    a = torch.from_numpy(a_star[:, None].copy()).cuda()
+    t0 = torch.from_numpy(t_star.copy()).cuda()
+    for k, dtp in enumerate(dts):
+        geo = engine.geometry_batch(dtp, a, theta)
+        lam_p = engine.solve_base_batch(geo.base, geo.dPdrho, t0, h, nth0=1, want_X=False, want_dX=False, want_matrix=False).lam.cpu().numpy()
+        np.testing.assert_allclose(pred[k], lam_p - tg.gamma, rtol=3e-3, atol=1e-12 * np.abs(tg.gamma).max() + 1e-14)
+    # (iii) single coefficients, central differences through the whole forward path
+    def gamma_of(tab_mn, tab_nyq):
+        dtx = engine.DeviceTables.from_host(dataclasses.replace(st, tab_mn=tab_mn, tab_nyq=tab_nyq))
+        geo = engine.geometry_batch(dtx, a, theta)
+        return engine.solve_base_batch(geo.base, geo.dPdrho, t0, h, nth0=1, want_X=False, want_dX=False, want_matrix=False).lam.cpu().numpy()
+    gmn, gnq = tg.grad_mn.cpu().numpy(), tg.grad_nyq.cpu().numpy()
+    for (which, row, mode) in (("mn", 0, 1), ("mn", 1, 14), ("mn", 2, 3), ("mn", 3, 1), ("nyq", 1, 0), ("nyq", 0, 2), ("nyq", 5, 1), ("nyq", 4, 17)):
+        base_tab = st.tab_mn if which == "mn" else st.tab_nyq
+        step = 1e-6 * max(np.abs(base_tab[:, row, mode]).max(), 1e-3)
+        tp, tm = base_tab.copy(), base_tab.copy()
+        tp[:, row, mode] += step; tm[:, row, mode] -= step
+        if which == "mn":
+            fd = (gamma_of(tp, st.tab_nyq) - gamma_of(tm, st.tab_nyq)) / (2 * step)
+            an = gmn[:, row, mode]
+        else:
+            fd = (gamma_of(st.tab_mn, tp) - gamma_of(st.tab_mn, tm)) / (2 * step)
+            an = gnq[:, row, mode]
+        np.testing.assert_allclose(an, fd, rtol=5e-3, atol=2e-3 * np.abs(fd).max() + 1e-12, err_msg=f"{which} row {row} mode {mode}")
