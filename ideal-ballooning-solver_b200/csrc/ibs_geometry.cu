@@ -58,6 +58,7 @@ struct GeoParams {
     int nfp;                // toroidal stride of the packed n index
     double phi_center, psi_e, L_ref;
     double* base_out; double* theta_vmec_out; int* info_out;
+    int fold;               // axisymmetric tables: allow the periodicity fold (IBS_GEO_FOLD=0 turns it off)
 };
 
 // ---- pack kernels: (ns, rows, mn) tables -> dense (m, n_idx) grid with the n-weights folded in -----------
@@ -190,7 +191,29 @@ geometry_kernel(const GeoParams p) {
     const int n_nyq = (NT2 > 0) ? p.M2 * (NT2 + 1) * ROWP_NYQ : p.M2 * W2 * ROW_NYQ;
     double* s_nyq = s_mn + n_mn;
     const int tid = threadIdx.x;
-    const int pts_per_surface = p.nalpha * p.nl;
+    // Periodicity fold (axisymmetric tables only).  Every mode sum is 2 pi-periodic in theta_vmec and does not depend on phi,
+    // and theta_vmec(theta_pest + 2 pi) = theta_vmec(theta_pest) + 2 pi, so grid points one poloidal turn apart share their
+    // Newton solve and their 19 sums; only the pointwise epilogue (secular shear term, phi) is per point.  The reference's
+    // own grids are commensurate: theta = linspace(-f pi, f pi, 2 mpol f + 1) (ball_scan.py:204-208) has 2 mpol points per
+    // turn.  Checked on the data, not assumed: P = rint(2 pi / (theta[1] - theta[0])) is used only if EVERY point satisfies
+    // theta[j] = theta[j mod P] + 2 pi (j div P) to 2e-12 (the grid need not be uniform).
+    int P = p.nl;
+    if constexpr (NT1 == 0 && NT2 == 0) {
+        if (p.fold && p.nl >= 3) {
+            const double TWO_PI = 6.283185307179586;
+            const double h0 = p.theta[1] - p.theta[0];
+            const double pf = (h0 > 0.0) ? TWO_PI / h0 : 0.0;
+            const int Pc = (pf >= 2.0 && pf < (double)p.nl) ? (int)rint(pf) : 0;
+            bool okf = Pc >= 2 && Pc < p.nl;
+            if (okf)
+                for (int j = tid; j < p.nl; j += GEO_THREADS) {
+                    const int q = j / Pc, r = j - q * Pc;
+                    okf &= fabs((p.theta[j] - p.theta[r]) - TWO_PI * (double)q) <= 2e-12;
+                }
+            if (__syncthreads_and(okf)) P = Pc;
+        }
+    }
+    const int pts_per_surface = p.nalpha * P;
     const int tiles_per_surface = (pts_per_surface + GEO_THREADS - 1) / GEO_THREADS;
     unsigned parity = 0;
     if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -223,7 +246,7 @@ geometry_kernel(const GeoParams p) {
         {
             const int pt = tile * GEO_THREADS + tid;
             if (pt >= pts_per_surface) continue;
-            const int ja = pt / p.nl, jl = pt - ja * p.nl;
+            const int ja = pt / P, jl = pt - ja * P;
             const double al = p.alpha_per_surface ? p.alpha[(size_t)js * p.nalpha + ja] : p.alpha[ja];
             const double theta_p = p.theta[jl];
             const double phi = p.phi_center + (theta_p - al) / iota;            // utils.py:373
@@ -492,7 +515,15 @@ geometry_kernel(const GeoParams p) {
             GeoSums g;
             g.R = R; g.R_s = R_s; g.R_t = R_t; g.R_p = R_p; g.Z_s = Z_s; g.Z_t = Z_t; g.Z_p = Z_p; g.L_s = L_s; g.L_t = L_t; g.L_p = L_p;
             g.sqrtg = sqrtg; g.B = B; g.B_s = B_s; g.B_t = B_t; g.B_p = B_p; g.Bsup_p = Bsup_p; g.Bsub_s = Bsub_s; g.Bsub_t = Bsub_t; g.Bsub_p = Bsub_p;
-            geo_point_epilogue(p, g, js, ja, jl, phi, th, nit, ok, s_val, iota, d_iota, dpds, shat);
+            if constexpr (NT1 == 0 && NT2 == 0) {
+                for (int jf = jl; jf < p.nl; jf += P) {           // the same sums zero, one, two, ... poloidal turns on
+                    const double tp = p.theta[jf];
+                    geo_point_epilogue(p, g, js, ja, jf, p.phi_center + (tp - al) / iota, th + (tp - theta_p), nit, ok, s_val, iota, d_iota,
+                                       dpds, shat);
+                }
+            } else {
+                geo_point_epilogue(p, g, js, ja, jl, phi, th, nit, ok, s_val, iota, d_iota, dpds, shat);
+            }
         }
     }
 }
@@ -880,6 +911,7 @@ int geometry_dispatch(const double* tab_mn, const double* tab_nyq, const double*
     p.theta = theta; p.nl = nl; p.ns = ns; p.M1 = M1; p.M2 = M2; p.nfp = nfp;
     p.phi_center = phi_center; p.psi_e = -phiedge / (2.0 * 3.141592653589793); p.L_ref = aminor_p;
     p.base_out = base_out; p.theta_vmec_out = theta_vmec_out; p.info_out = info_out;
+    { const char* e = std::getenv("IBS_GEO_FOLD"); p.fold = !(e && e[0] == '0'); }
     if (info_out) IBS_CUDA_CHECK(cudaMemsetAsync(info_out, 0, (size_t)ns * nalpha * sizeof(int), st));
     int rc;
     if (NT1 == 0) rc = launch_geometry<0, 0>(p, st);

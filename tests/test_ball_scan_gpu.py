@@ -134,21 +134,41 @@ def test_table_gradient_reverse_mode_k1(cuda_lib):
         geo = engine.geometry_batch(dtp, a, theta)
         lam_p = engine.solve_base_batch(geo.base, geo.dPdrho, t0, h, nth0=1, want_X=False, want_dX=False, want_matrix=False).lam.cpu().numpy()
         np.testing.assert_allclose(pred[k], lam_p - tg.gamma, rtol=3e-3, atol=1e-12 * np.abs(tg.gamma).max() + 1e-14)
-    # (iii) single coefficients, central differences through the whole forward path
+    # (iii) single coefficients: the reverse-mode chain against the same first-order quantity formed the long way (K1 on the
+    # perturbed tables, exact delta g, c, f, then the Hellmann-Feynman sums) -- this isolates the adjoint of K1 from the
+    # O(h^2) difference between the continuum Hellmann-Feynman formula (utils.py:1676-1680) and the discrete eigenvalue
+    singles = (("mn", 0, 1), ("mn", 1, 14), ("mn", 2, 3), ("mn", 3, 1), ("mn", 4, 9), ("mn", 5, 20), ("mn", 2, 30),
+               ("nyq", 1, 0), ("nyq", 0, 2), ("nyq", 5, 1), ("nyq", 4, 17), ("nyq", 2, 5), ("nyq", 3, 11), ("nyq", 6, 40))
+    gmn, gnq = tg.grad_mn.cpu().numpy(), tg.grad_nyq.cpu().numpy()
+    sets, steps, an = [], [], []
+    for (which, row, mode) in singles:
+        base_tab = st.tab_mn if which == "mn" else st.tab_nyq
+        step = max(1e-4 * np.abs(base_tab[:, row, mode]).max(), 1e-5)      # (g, c, f carry ~1e-16 of rounding: keep noise / step small)
+        for sgn in (+1.0, -1.0):
+            tp = base_tab.copy()
+            tp[:, row, mode] += sgn * step
+            sets.append(dataclasses.replace(st, tab_mn=tp) if which == "mn" else dataclasses.replace(st, tab_nyq=tp))
+        steps.append(step)
+        an.append((gmn if which == "mn" else gnq)[:, row, mode])
+    hf1 = scan.hellmann_feynman_gamma(dt0, [engine.DeviceTables.from_host(x) for x in sets], a_star, t_star, theta)
+    for k, sgl in enumerate(singles):
+        long_way = (hf1.dgamma[2 * k] - hf1.dgamma[2 * k + 1]) / (2.0 * steps[k])
+        np.testing.assert_allclose(an[k], long_way, rtol=2e-4, atol=1e-4 * np.abs(long_way).max() + 1e-13, err_msg=str(sgl))
+    # ... and central differences of lambda itself through the whole forward path for low-order coefficients (where the
+    # continuum formula is accurate to ~1e-3 on this grid)
     def gamma_of(tab_mn, tab_nyq):
         dtx = engine.DeviceTables.from_host(dataclasses.replace(st, tab_mn=tab_mn, tab_nyq=tab_nyq))
         geo = engine.geometry_batch(dtx, a, theta)
         return engine.solve_base_batch(geo.base, geo.dPdrho, t0, h, nth0=1, want_X=False, want_dX=False, want_matrix=False).lam.cpu().numpy()
-    gmn, gnq = tg.grad_mn.cpu().numpy(), tg.grad_nyq.cpu().numpy()
-    for (which, row, mode) in (("mn", 0, 1), ("mn", 1, 14), ("mn", 2, 3), ("mn", 3, 1), ("nyq", 1, 0), ("nyq", 0, 2), ("nyq", 5, 1), ("nyq", 4, 17)):
+    for (which, row, mode) in (("mn", 0, 0), ("mn", 0, 1), ("nyq", 1, 0), ("nyq", 0, 0)):
         base_tab = st.tab_mn if which == "mn" else st.tab_nyq
-        step = 1e-6 * max(np.abs(base_tab[:, row, mode]).max(), 1e-3)
+        step = max(1e-6 * np.abs(base_tab[:, row, mode]).max(), 5e-6)      # lambda carries ~1e-14 of rounding: keep noise / step small
         tp, tm = base_tab.copy(), base_tab.copy()
         tp[:, row, mode] += step; tm[:, row, mode] -= step
         if which == "mn":
             fd = (gamma_of(tp, st.tab_nyq) - gamma_of(tm, st.tab_nyq)) / (2 * step)
-            an = gmn[:, row, mode]
+            ana = gmn[:, row, mode]
         else:
             fd = (gamma_of(st.tab_mn, tp) - gamma_of(st.tab_mn, tm)) / (2 * step)
-            an = gnq[:, row, mode]
-        np.testing.assert_allclose(an, fd, rtol=5e-3, atol=2e-3 * np.abs(fd).max() + 1e-12, err_msg=f"{which} row {row} mode {mode}")
+            ana = gnq[:, row, mode]
+        np.testing.assert_allclose(ana, fd, rtol=1e-2, atol=5e-3 * np.abs(fd).max() + 1e-12, err_msg=f"{which} row {row} mode {mode}")

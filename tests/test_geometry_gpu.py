@@ -122,3 +122,64 @@ def test_argmax_guards_bit_exact(cuda_lib):
         want = -1 if ia < 0 else ia * 15 + it
         assert idx[k].item() == want
         assert sig[k].item() == s0
+
+
+def _d3d_tables(ns=5, seed=3):
+    from ideal_ballooning_solver_b200 import synthetic, tables
+    return tables.RadialSplines(synthetic.make_equilibrium("d3d", seed=seed)).evaluate(np.linspace(0.3, 0.9, ns))
+
+
+def _geometry_with_fold(st, alpha, theta, fold, monkeypatch):
+    import torch
+    from ideal_ballooning_solver_b200 import engine as eng
+    monkeypatch.setenv("IBS_GEO_FOLD", "1" if fold else "0")          # read by every ibs_geometry_batch call
+    dt = eng.DeviceTables.from_host(st)
+    geo = eng.geometry_batch(dt, torch.from_numpy(alpha).cuda(), torch.from_numpy(theta).cuda(), want_theta_vmec=True, want_info=True)
+    return geo.base.cpu().numpy(), geo.theta_vmec.cpu().numpy(), geo.info.cpu().numpy(), geo.dPdrho.cpu().numpy()
+
+
+@pytest.mark.parametrize("grid", ["reference", "bench", "ragged_tail", "nonuniform_periodic"])
+def test_axisymmetric_periodicity_fold_matches_direct(cuda_lib, monkeypatch, grid):
+    """Axisymmetric tables: points one poloidal turn apart share their Newton solve and mode sums (K1's periodicity fold).
+    The folded evaluation must agree with the point-by-point one to rounding on the reference's own grid
+    (ball_scan.py:204-208: 2 mpol points per turn), on the bench grid, on a grid whose last turn is incomplete and on a
+    non-uniform periodic grid."""
+    st = _d3d_tables()
+    mpol = int(st.xm.max()) + 1
+    if grid == "reference":
+        fac = 3
+        theta = np.linspace(-fac * np.pi, fac * np.pi, 2 * mpol * fac + 1)
+    elif grid == "bench":
+        theta = np.linspace(-4 * np.pi, 4 * np.pi, 1025)
+    elif grid == "ragged_tail":
+        theta = -3 * np.pi + (2 * np.pi / 96) * np.arange(96 * 3 + 41)
+    else:
+        one = np.sort(np.random.default_rng(0).uniform(0.0, 2 * np.pi, 77)); one[0] = 0.0
+        one = np.concatenate([[0.0, 2 * np.pi / 90], one[2:]])        # theta[1] - theta[0] = 2 pi / 90 -> P = 90 is NOT the period (77): no fold
+        theta = np.concatenate([one - 2 * np.pi, one, one + 2 * np.pi])
+    alpha = np.array([0.0, 0.7, 2.9])
+    b1, t1, i1, d1 = _geometry_with_fold(st, alpha, theta, True, monkeypatch)
+    b0, t0, i0, d0 = _geometry_with_fold(st, alpha, theta, False, monkeypatch)
+    assert np.all((i0 >> 16) == 0) and np.all((i1 >> 16) == 0)
+    if grid == "nonuniform_periodic":
+        assert np.array_equal(b1, b0) and np.array_equal(t1, t0)      # candidate period rejected by the data check: same code path
+        return
+    np.testing.assert_allclose(t1, t0, rtol=0, atol=2e-13)
+    scale = np.max(np.abs(b0), axis=-1, keepdims=True)
+    assert np.max(np.abs(b1 - b0) / scale) < 1e-12
+    np.testing.assert_allclose(d1, d0, rtol=1e-12)
+
+
+def test_periodicity_fold_ignores_3d_tables_and_incommensurate_grids(cuda_lib, monkeypatch):
+    from ideal_ballooning_solver_b200 import synthetic, tables
+    st = _d3d_tables()
+    theta = np.linspace(-4.1 * np.pi, 4.1 * np.pi, 1025)               # 2 pi / h is not an integer
+    alpha = np.array([0.3])
+    b1, t1, _, _ = _geometry_with_fold(st, alpha, theta, True, monkeypatch)
+    b0, t0, _, _ = _geometry_with_fold(st, alpha, theta, False, monkeypatch)
+    assert np.array_equal(b1, b0) and np.array_equal(t1, t0)
+    st3 = tables.RadialSplines(synthetic.make_equilibrium("ncsx", seed=3)).evaluate(np.linspace(0.4, 0.8, 3))
+    theta = np.linspace(-4 * np.pi, 4 * np.pi, 513)
+    b1, t1, _, _ = _geometry_with_fold(st3, alpha, theta, True, monkeypatch)
+    b0, t0, _, _ = _geometry_with_fold(st3, alpha, theta, False, monkeypatch)
+    assert np.array_equal(b1, b0) and np.array_equal(t1, t0)
