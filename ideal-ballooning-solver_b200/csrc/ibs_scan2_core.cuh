@@ -288,6 +288,12 @@ IBS_HD void out_join(const Sweep& f, const Sweep& b, const Rec& rk, double th0, 
     const double sX0 = zf2 * (w43 * f.a0o + w23 * f.a0e) + zb2 * (w43 * b.a0o + w23 * b.a0e) - wk * tk;
     const double sX1 = zf2 * (w43 * f.a1o + w23 * f.a1e) + zb2 * (w43 * b.a1o + w23 * b.a1e) - wk * Fk;
     o.gam = lam + (sX0 - 2.0 * sD) / sX1;
+    // the same pass seen as an iteration pass (eval_join): twisted residual at row k and S = sum F z^2 with z_k = 1
+    {
+        const double r = -(f.w * zf + b.w * zb + tk);
+        const double S = fma(zf2, f.a1o + f.a1e, zb2 * (b.a1o + b.a1e)) - Fk;
+        o.dlt = r / S;
+    }
     const double mf = f.vmax * fabs(zf), mb = b.vmax * fabs(zb);
     o.zmax = fmax(mf, mb);
     o.jmax = (mb > mf) ? b.jmax : f.jmax;
@@ -302,23 +308,26 @@ IBS_HD void solve_item2(Ctx& ctx, const ItemProblem& P, double th0, bool act, do
                         ItemResult& res, ColdState<1>& cs) {
     const double scale = fmax(fabs(P.U), 1e-3);
     const double tol = 1.7763568394002505e-15 * scale, tol_stag = 1e-10 * scale;
+    const double tol_lvl = 1e-9 * scale;                  // coarse levels: the error left in the level's eigenvalue
     const double qnan = NAN;
     const int N = P.N;
     Iter& it = cs.it[0];
     SolveOut& out = cs.out[0];
-    double& rho1 = cs.rho1[0]; double& rho2 = cs.rho2[0]; double& rbest = cs.rbest[0];
+    double& rho1 = cs.rho1[0]; double& rho2 = cs.rho2[0]; double& rho3 = cs.rho3[0]; double& rbest = cs.rbest[0];
+    double& Cq = cs.Cq[0];
     int& nev = cs.nev[0]; int& flags = cs.flags[0];
     bool& fin = cs.fin[0]; bool& wr = cs.wr[0]; bool& need = cs.need[0];
     double sh, r = 0.0, S = 1.0;
     int nodes = 0;
     const bool want_out = P.want_X || P.want_dX;
-    rho1 = qnan; rho2 = qnan; nev = 0; flags = 0; fin = false; wr = false; need = false; rbest = qnan;
+    rho1 = qnan; rho2 = qnan; rho3 = qnan; Cq = 0.0; nev = 0; flags = 0; fin = false; wr = false; need = false; rbest = qnan;
     iter_init(it, qnan, P.Lb, P.U, false);
     sh = it.lam;
     res.gam = qnan; res.rho = qnan;
     int lev = P.nlev, Nl = level_n(N, lev), k = snap_k((Nl - 1) / 2, Nl), round = 0;
     int phase = PH_ITER;
     bool lowq_any = false, fix_any = false;
+    bool prov = false;              // fine level: the first output pass doubles as the confirming iteration pass
     int jsel = -1;
     for (;;) {
         const int kind = (phase == PH_ITER || phase == PH_SIGMA) ? 1 : (phase == PH_PEAK || phase == PH_O1) ? 2 : 3;
@@ -330,12 +339,25 @@ IBS_HD void solve_item2(Ctx& ctx, const ItemProblem& P, double th0, bool act, do
                 if (need && nodes + (r > 0.0 ? 1 : 0) > 1) flags |= FLAG_SIGMA_NOT_MAX;
                 break;
             }
-            if (!it.done) nev += (1 << MAXLEV) >> lev;
-            iter_update(it, r, S, nodes, P.U, tol, tol_stag, (lev > 0) ? 1e-7 * scale : tol, lev == 0);
+            const bool fine = lev == 0;
+            if (!it.done) {
+                nev += (1 << MAXLEV) >> lev;
+                const double dp0 = it.dprev;
+                iter_update(it, r, S, nodes, P.U, fine ? tol : tol_lvl, tol_stag, fine ? tol : 1e-7 * scale, true);
+                // Each pass restarts from e_k, so the error obeys e' = C e^2 with C a property of the spectrum and of the
+                // matching row (about the same on every level): two consecutive in-basin corrections measure it ...
+                if (nodes == 0 && dp0 < 1e-2 * scale && it.dprev < 0.1 * dp0 && it.dprev > 0.0) Cq = it.dprev / (dp0 * dp0);
+                // ... and on the next levels ONE pass is enough when the error it leaves, C dl^2, is predicted (x 10) below
+                // what the extrapolation to the finer level can use
+                if (!it.done && !fine && it.rq && Cq > 0.0 && 10.0 * Cq * it.dprev * it.dprev <= tol_lvl) { it.done = true; it.conv = true; }
+            }
             sh = it.lam;
-            if (!ctx.all(it.done)) continue;
+            // Fine level: after an in-basin step whose successor is predicted tiny (q = C dl), go straight to the first output
+            // pass at lam + dl -- it IS an iteration pass (out_join returns its correction) and confirms or rejects the step
+            const bool ready = it.done || (fine && it.rq && Cq > 0.0 && 10.0 * Cq * it.dprev <= 1e-5);
+            if (!ctx.all(ready)) continue;
             if (lev > 0) {
-                rho2 = rho1; rho1 = (it.conv && it.rho == it.rho) ? it.rho : qnan;
+                rho3 = rho2; rho2 = rho1; rho1 = (it.conv && it.rho == it.rho) ? it.rho : qnan;
                 if (lev == P.nlev) {
                     sh = (rho1 == rho1) ? rho1 : it.lam;
                     phase = PH_PEAK;
@@ -343,9 +365,10 @@ IBS_HD void solve_item2(Ctx& ctx, const ItemProblem& P, double th0, bool act, do
                 }
             } else {
                 if (!fin) {
-                    rbest = (it.conv && it.rho == it.rho) ? it.rho : it.lam;
+                    prov = !it.done;
+                    rbest = (!it.done || (it.conv && it.rho == it.rho)) ? it.rho : it.lam;       // (provisional: it.lam = it.rho)
                     sh = rbest;
-                    if (!it.conv) flags |= FLAG_NOT_CONVERGED;
+                    if (it.done && !it.conv) flags |= FLAG_NOT_CONVERGED;
                 }
                 phase = PH_O1;
                 continue;
@@ -355,6 +378,25 @@ IBS_HD void solve_item2(Ctx& ctx, const ItemProblem& P, double th0, bool act, do
             const int kp = (jlo + jhi) / 2, km = (Nl - 1) / 2;
             k = snap_k((kp > km ? kp - km : km - kp) * PEAK_SNAP <= Nl ? km : kp, Nl);
         } else if (phase == PH_O1) {
+            bool retry = false;
+            if (prov && !fin) {
+                // the confirming pass: d1 = |correction at lam + d0|.  Accept at the rounding level, or when d1 / d0 = q says
+                // both that the eigenvalue after this correction is exact (d1 q^2 <= tol, the iteration's own predictive
+                // stop) and that the eigenvector of THIS pass is clean (its contamination is ~ C d1 = q^2 <= 1e-10)
+                const double d1 = fabs(out.dlt), d0 = it.dprev, q = d1 / d0;
+                const bool acc = out.bad || d1 <= tol || (d1 < tol_stag && d1 >= 0.25 * d0) || (q <= 1e-5 && d1 * q * q <= tol);
+                if (acc) {
+                    if (!out.bad && out.dlt == out.dlt) rbest = sh + out.dlt;
+                    it.done = true; it.conv = true; it.rho = rbest;
+                } else {
+                    retry = true;                             // go on iterating from here (an in-basin step when it is one)
+                    it.lo = fmax(it.lo, sh);
+                    if (out.dlt > 0.0 && sh + out.dlt <= it.hi) { it.lam = sh + out.dlt; it.dprev = d1; }
+                    Cq = 0.0;
+                }
+                prov = false;
+            }
+            if (ctx.any(retry)) { sh = it.lam; phase = PH_ITER; continue; }
             const bool lowq = !fin && !out.bad && out.zmax > LOWQ && round < 3;
             const bool newly = !fin && !lowq;
             if (newly) {
@@ -376,8 +418,13 @@ IBS_HD void solve_item2(Ctx& ctx, const ItemProblem& P, double th0, bool act, do
             --lev;
             Nl = level_n(N, lev);
             k = snap_k(2 * k, Nl);
+            // start of the finer level: the eigenvalue is lam* + a h^2 + b h^4 + ...; two known levels remove a, three a and b
             double l0 = rho1;
-            if (rho2 == rho2) l0 = rho1 - 0.25 * (rho2 - rho1);      // Richardson: the error is ~ h^2
+            if (rho2 == rho2) {
+                const double d12 = rho1 - rho2, d23 = rho2 - rho3;
+                l0 = rho1 + 0.25 * d12;
+                if (rho3 == rho3 && fabs(d23) > 2.0 * fabs(d12) && fabs(d23) < 8.0 * fabs(d12)) l0 = rho1 + 0.3125 * d12 - 0.015625 * d23;
+            }
             iter_init(it, l0, P.Lb, P.U, false);
             sh = it.lam;
             phase = PH_ITER;
@@ -386,6 +433,7 @@ IBS_HD void solve_item2(Ctx& ctx, const ItemProblem& P, double th0, bool act, do
         if (ctx.any(lowq_any)) {
             k = snap_k(ctx.first_i(jsel), N);
             lowq_any = false;
+            Cq = 0.0;                                         // (a property of the matching row too)
             iter_init(it, sh, P.Lb, P.U, fin);
             if (!fin) sh = it.lam;
             phase = PH_ITER;

@@ -435,6 +435,7 @@ struct Sweep {
 
 struct SolveOut {                 // what the output pass returns per solve
     double gam, zmax; int jmax; bool bad;
+    double dlt;                        // lane-per-chain kernel: the Rayleigh-quotient correction r / S of this pass's shift (out_join)
     double xkf, xkb; int Ekf, Ekb;     // the two sweeps at the matching row: value and scale exponent
 };
 
@@ -823,11 +824,12 @@ struct Iter {
     double lam, rho, lo, hi, b1, N1, b2, N2, dprev;
     int nabove, it;
     bool collapsed, done, conv, warm;
+    bool rq;        // the last update took the in-basin Rayleigh-quotient step (lam = rho); dprev = the size of that step
 };
 
 IBS_HD void iter_init(Iter& s, double l0, double Lb, double U, bool frozen) {
     s.lo = Lb; s.hi = U; s.b1 = s.N1 = s.b2 = s.N2 = 0.0; s.dprev = 1e300; s.nabove = 0; s.it = 0;
-    s.collapsed = false; s.done = frozen; s.conv = frozen;
+    s.collapsed = false; s.done = frozen; s.conv = frozen; s.rq = false;
     s.warm = (l0 > Lb && l0 < U);
     s.lam = s.warm ? l0 : U;
     s.rho = s.lam;
@@ -851,6 +853,7 @@ IBS_HD void iter_update(Iter& s, double r, double S, int nodes, double U, double
         if (inbasin && rho == rho) s.lo = fmax(s.lo, fmin(rho, s.hi));
     }
     bool done = false;
+    s.rq = false;
     if (pos) {
         const double dl = fabs(rho - lam);
         if (dl <= stop || (dl < tol_stag && dl >= 0.25 * s.dprev)) { s.conv = true; done = true; }
@@ -869,6 +872,7 @@ IBS_HD void iter_update(Iter& s, double r, double S, int nodes, double U, double
             s.collapsed = true;
         } else if (inbasin && rho > lam && rho <= s.hi) {
             nxt = rho;
+            s.rq = true;
         } else if (above) {
             double pw = 0.5;
             if (s.nabove >= 2 && s.N1 - s.N2 > 0.0) pw = (s.b1 - s.b2) / (s.N1 - s.N2);
@@ -902,6 +906,7 @@ struct ColdState {
     Iter it[SPL];
     SolveOut out[SPL];
     double rho1[SPL], rho2[SPL], rbest[SPL];
+    double rho3[SPL], Cq[SPL];          // lane-per-chain kernel: third level for the extrapolation, quadratic-convergence constant
     int nev[SPL], flags[SPL];
     bool fin[SPL], wr[SPL], need[SPL];
 };

@@ -2,6 +2,8 @@
 // a time, the two lanes of the pair (forward chain, mirrored backward chain) one after the other, with records read
 // straight from memory.  TEST INFRASTRUCTURE ONLY (tests/test_scan_core_host.py); not part of the library.
 //   g++ -O2 -std=c++17 -shared -fPIC -o scan2_core_host.so tools/scan2_core_host.cpp
+#include <cstdio>
+#include <cstdlib>
 #include "scan_core_host.cpp"        // the preparation (scan_host_prep) and the two-chains-per-lane harness
 #include "../ideal-ballooning-solver_b200/csrc/ibs_scan2_core.cuh"
 
@@ -12,6 +14,7 @@ struct Host2Ctx {
     const double* line_base; int N;
     const double* lvl = nullptr; int Nl = 0; int h = 0;
     long passes = 0; double cost = 0.0;
+    int nev_lev[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // iteration passes per level (instrumentation for tools/iter_hist.py)
     void begin_pass(int lev, int Nl_, int) { lvl = line_base + (size_t)level_offset(N, lev) * REC; Nl = Nl_; }
     void wait(int) {}
     void release(int) {}
@@ -23,6 +26,8 @@ struct Host2Ctx {
         h = 0; const EvalEnd f = eval_lane(*this, lev, Nl_, qf, qm, th0, lam);
         h = 1; const EvalEnd b = eval_lane(*this, lev, Nl_, qb, qm, th0, lam);
         eval_join(f, b, rec_k(k), th0, lam, r, S, nodes);
+        nev_lev[lev & 7] += 1;
+        if (getenv("IBS_HOST_TRACE")) printf("  lev %d Nl %d k %d lam %.15g rho %.15g r %.3e S %.3e nodes %d\n", lev, Nl_, k, lam, lam + r / S, r, S, nodes);
         passes += 1; cost += (double)Nl_ / N;
     }
     void out1(int lev, int Nl_, int k, double th0, double lam, SolveOut& out) {
@@ -30,6 +35,8 @@ struct Host2Ctx {
         h = 0; const Sweep f = out_lane<false>(*this, lev, Nl_, qf, qm, false, th0, lam, 0.0, 0, nullptr);
         h = 1; const Sweep b = out_lane<false>(*this, lev, Nl_, qb, qm, true, th0, lam, 0.0, 0, nullptr);
         out_join(f, b, rec_k(k), th0, lam, k, out);
+        if (lev == 0) nev_lev[7] += 1;                       // first output passes on the fine level (slot 7 of the counts)
+        if (getenv("IBS_HOST_TRACE")) printf("  O1 lev %d k %d lam %.15g dlt %.3e gam %.15g zmax %.3e\n", lev, k, lam, out.dlt, out.gam, out.zmax);
         passes += 1; cost += (double)Nl_ / N;
     }
     void out2(int lev, int Nl_, int k, double th0, double lam, const SolveOut& out, double* Xw) {
@@ -50,7 +57,14 @@ struct Host2Ctx {
         if (flag) fixup_solve(*this, X, want_dX ? dX : nullptr, N_, bad, hh, 0, 1);
     }
 };
+std::vector<int> g_counts2;
 }  // namespace
+
+// iteration passes per (solve, level) of the last scan2_host_solve call: out[nsolve][8]
+extern "C" long scan2_host_eval_counts(int* out) {
+    for (size_t i = 0; i < g_counts2.size(); ++i) out[i] = g_counts2[i];
+    return (long)g_counts2.size();
+}
 
 extern "C" int scan2_host_size_ok(int N) { return scan2_size_ok(N) ? 1 : 0; }
 
@@ -59,6 +73,7 @@ extern "C" long scan2_host_solve(const double* poly, const double* bounds, const
                                  double* dX_out, int* info_out) {
     const int nlev = num_levels(N), rows_total = level_offset(N, nlev + 1);
     long passes = 0; double cost = 0.0;
+    g_counts2.assign((size_t)nline * nth0 * 8, 0);
     for (int line = 0; line < nline; ++line)
         for (int i = 0; i < nth0; ++i) {
             const size_t s = (size_t)line * nth0 + i;
@@ -75,6 +90,7 @@ extern "C" long scan2_host_solve(const double* poly, const double* bounds, const
             if (lam_matrix_out) lam_matrix_out[s] = res.rho;
             if (info_out) info_out[s] = res.info;
             passes += ctx.passes; cost += ctx.cost;
+            for (int l = 0; l < 8; ++l) g_counts2[s * 8 + l] = ctx.nev_lev[l];
         }
     g_cost = cost;
     return passes;
