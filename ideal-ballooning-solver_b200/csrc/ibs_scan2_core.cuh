@@ -33,6 +33,8 @@ constexpr int NH = 16;            // solves per warp
 constexpr int T0 = TR + 3;        // records of stage 0: steps 0 .. 34
 constexpr int NPRE = 5;           // steps 0 .. 4 are done one at a time (start values, the end-point stencils); chunks start at step 5
 constexpr int KQ = 16;            // chain ends (and chunk ends) are multiples of KQ
+constexpr int WREC = MAXLEV + 2;  // warm-start record: the eigenvalue of every level (index = level) + how far the neighbour was
+constexpr double WARM_FAR = 0.05; // relative distance of the coarsest-level eigenvalues beyond which a neighbour is no help
 
 IBS_HD int stage_of(int q) { return q < T0 ? 0 : (q - 3) / TR; }
 IBS_HD int stage_first(int s) { return s == 0 ? 0 : TR * s + 3; }
@@ -302,10 +304,19 @@ IBS_HD void out_join(const Sweep& f, const Sweep& b, const Rec& rk, double th0, 
 
 // ---- the state machine of one solve (both lanes of a pair run it identically) -----------------------------------------
 // Ctx supplies:  eval(lev, Nl, k, th0, lam, r, S, nodes);  out1(lev, Nl, k, th0, lam, SolveOut&);  out2(lev, Nl, k, th0, lam,
-// SolveOut, Xw);  all / any / min_i / max_i / first_i;  fixup(wr, X, dX, N, bad, h, want_dX)
+// SolveOut, Xw);  all / any / min_i / max_i / first_i;  fixup(wr, X, dX, N, bad, h, want_dX);
+// warm_in(token, lev) / warm_out(token, lev, value): the per-level eigenvalues of the theta0 NEIGHBOUR (one grid step away,
+// solved earlier: token w_in, -1 = none) and of this solve for its own neighbour (token w_out, -1 = nobody needs them).
+//
+// Warm start.  lam_max is smooth in theta0, and so is the error of every start value below: with the neighbour's level
+// eigenvalues n_l known, the coarsest level starts at n_nlev instead of the Gershgorin bound (~4 passes instead of ~15),
+// and every finer level starts at  E(own coarser levels) + [ n_l - E(neighbour's coarser levels) ]  -- the extrapolation E
+// corrected by the error it made for the neighbour.  Whether the neighbour is close enough for that (adjacent surfaces of a
+// tokamak scan: ~1 %; adjacent alphas of a stellarator scan: ~30 %, useless) is measured on the coarsest level, |lam - n| /
+// |lam| <= WARM_FAR, and handed on with the record: a solve whose predecessor found its own neighbour far starts cold.
 template <class Ctx>
 IBS_HD void solve_item2(Ctx& ctx, const ItemProblem& P, double th0, bool act, double sigma, bool has_sigma, double* Xrow, double* dXrow,
-                        ItemResult& res, ColdState<1>& cs) {
+                        ItemResult& res, ColdState<1>& cs, int w_in = -1, int w_out = -1) {
     const double scale = fmax(fabs(P.U), 1e-3);
     const double tol = 1.7763568394002505e-15 * scale, tol_stag = 1e-10 * scale;
     const double tol_lvl = 1e-9 * scale;                  // coarse levels: the error left in the level's eigenvalue
@@ -321,7 +332,11 @@ IBS_HD void solve_item2(Ctx& ctx, const ItemProblem& P, double th0, bool act, do
     int nodes = 0;
     const bool want_out = P.want_X || P.want_dX;
     rho1 = qnan; rho2 = qnan; rho3 = qnan; Cq = 0.0; nev = 0; flags = 0; fin = false; wr = false; need = false; rbest = qnan;
-    iter_init(it, qnan, P.Lb, P.U, false);
+    cs.wi[0] = w_in; cs.wo[0] = w_out;
+    {
+        const double n4 = ctx.warm_in(w_in, P.nlev);
+        iter_init(it, (ctx.warm_in(w_in, MAXLEV + 1) > WARM_FAR) ? qnan : n4, P.Lb, P.U, false);
+    }
     sh = it.lam;
     res.gam = qnan; res.rho = qnan;
     int lev = P.nlev, Nl = level_n(N, lev), k = snap_k((Nl - 1) / 2, Nl), round = 0;
@@ -358,7 +373,13 @@ IBS_HD void solve_item2(Ctx& ctx, const ItemProblem& P, double th0, bool act, do
             if (!ctx.all(ready)) continue;
             if (lev > 0) {
                 rho3 = rho2; rho2 = rho1; rho1 = (it.conv && it.rho == it.rho) ? it.rho : qnan;
+                ctx.warm_out(cs.wo[0], lev, rho1);
                 if (lev == P.nlev) {
+                    // how far was the neighbour?  (far or unknown: no corrections from it on the finer levels either)
+                    const double n4 = ctx.warm_in(cs.wi[0], lev);
+                    const double far = fabs(rho1 - n4) / fmax(fabs(rho1), 0.05 * scale);
+                    if (!(far <= WARM_FAR)) cs.wi[0] = -1;
+                    ctx.warm_out(cs.wo[0], MAXLEV + 1, (far == far) ? far : 0.0);
                     sh = (rho1 == rho1) ? rho1 : it.lam;
                     phase = PH_PEAK;
                     continue;
@@ -404,6 +425,7 @@ IBS_HD void solve_item2(Ctx& ctx, const ItemProblem& P, double th0, bool act, do
                 res.gam = out.bad ? qnan : out.gam;
                 res.rho = out.bad ? qnan : rbest;
                 if (out.bad) flags = FLAG_BAD_INPUT;
+                ctx.warm_out(cs.wo[0], 0, res.rho);
             }
             jsel = lowq ? out.jmax : -1;
             lowq_any = lowq;
@@ -420,10 +442,25 @@ IBS_HD void solve_item2(Ctx& ctx, const ItemProblem& P, double th0, bool act, do
             k = snap_k(2 * k, Nl);
             // start of the finer level: the eigenvalue is lam* + a h^2 + b h^4 + ...; two known levels remove a, three a and b
             double l0 = rho1;
+            int order = 1;
             if (rho2 == rho2) {
                 const double d12 = rho1 - rho2, d23 = rho2 - rho3;
                 l0 = rho1 + 0.25 * d12;
-                if (rho3 == rho3 && fabs(d23) > 2.0 * fabs(d12) && fabs(d23) < 8.0 * fabs(d12)) l0 = rho1 + 0.3125 * d12 - 0.015625 * d23;
+                order = 2;
+                if (rho3 == rho3 && fabs(d23) > 2.0 * fabs(d12) && fabs(d23) < 8.0 * fabs(d12)) { l0 = rho1 + 0.3125 * d12 - 0.015625 * d23; order = 3; }
+            }
+            {
+                // the same extrapolation on the neighbour's levels, and the error it made there
+                const int wi = cs.wi[0];
+                const double n0 = ctx.warm_in(wi, lev), n1 = ctx.warm_in(wi, lev + 1);
+                double e = n1;
+                if (order >= 2) {
+                    const double n2 = ctx.warm_in(wi, lev + 2), d12 = n1 - n2;
+                    e = n1 + 0.25 * d12;
+                    if (order == 3) e = n1 + 0.3125 * d12 - 0.015625 * (n2 - ctx.warm_in(wi, lev + 3));
+                }
+                const double corr = n0 - e;
+                if (corr == corr && l0 == l0) l0 += corr;            // (NaN: no neighbour, or one of its levels did not converge)
             }
             iter_init(it, l0, P.Lb, P.U, false);
             sh = it.lam;

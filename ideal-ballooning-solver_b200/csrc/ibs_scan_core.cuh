@@ -824,7 +824,7 @@ struct Iter {
     double lam, rho, lo, hi, b1, N1, b2, N2, dprev;
     int nabove, it;
     bool collapsed, done, conv, warm;
-    bool rq;        // the last update took the in-basin Rayleigh-quotient step (lam = rho); dprev = the size of that step
+    bool rq;        // the last update took the full Rayleigh-quotient step (lam = rho; in the basin, or from just above); dprev = its size
 };
 
 IBS_HD void iter_init(Iter& s, double l0, double Lb, double U, bool frozen) {
@@ -882,6 +882,7 @@ IBS_HD void iter_update(Iter& s, double r, double S, int nodes, double U, double
             if (s.N2 < 0.05 * (U - s.b2)) pw = 1.0;
             nxt = s.b2 - pw * s.N2;
             if (!(nxt >= s.lo && nxt < s.hi)) nxt = 0.5 * (s.lo + s.hi);
+            else if (pw == 1.0) s.rq = true;               // the full Rayleigh-quotient step, taken from above
         } else {
             nxt = 0.5 * (s.lo + s.hi);
         }
@@ -907,6 +908,7 @@ struct ColdState {
     SolveOut out[SPL];
     double rho1[SPL], rho2[SPL], rbest[SPL];
     double rho3[SPL], Cq[SPL];          // lane-per-chain kernel: third level for the extrapolation, quadratic-convergence constant
+    int wi[SPL], wo[SPL];               // lane-per-chain kernel: tokens of the warm-start records read / written (-1: none)
     int nev[SPL], flags[SPL];
     bool fin[SPL], wr[SPL], need[SPL];
 };

@@ -11,6 +11,7 @@
 //                      (broadcast LDS.128) and advances its own solve.  No shuffles in the passes, no block barriers, no
 //                      per-solve set-up; the state no loop touches lives in shared memory (one block per thread); HBM
 //                      traffic is the records once (they stay in L2 for the ~23 passes of an item) plus the outputs.
+#include <cmath>
 #include <cstdlib>
 
 #include "ibs_common.cuh"
@@ -41,8 +42,10 @@ struct ScanParams {
     const double* theta0;     // [nline * nth0]
     const double* sigma;      // nullable
     int nline, nth0, N, nlev, rows_total, groups, nitems;
+    int lc, rounds;           // lane-per-chain kernel: lines per round and rounds of the column order (nitems = rounds * lc * groups, padded)
     double h;
     double* lam_out; double* lam_matrix_out; double* X_out; double* dX_out; int* info_out;
+    double* warm; unsigned* warm_flag;     // lane-per-chain kernel: [nline * groups][16][WREC] warm-start records handed to the next line, [nline * groups] ready flags (zeroed); null: off
     double* X_rows;           // where the eigenfunctions go: X_out, or scratch when only dX is wanted (null: no eigenfunction output)
     double* shift_ws; int* info_ws;      // two-kernel form: converged shift and counters handed from the iteration kernel to the output kernel
     unsigned* counter;
@@ -277,7 +280,14 @@ struct Dev2Ctx {
     double* ring; uint64_t* bars; unsigned parity; int lane, h;
     const double* line_base; int N;
     const double* lvl; int Nl, nst;
+    double* warm;                                            // warm-start records (global memory); tokens are element offsets
 
+    __device__ __forceinline__ double warm_in(int token, int lev) const {
+        return (token >= 0 && lev <= MAXLEV + 1) ? __ldcg(warm + token + lev) : __longlong_as_double(0x7ff8000000000000LL);
+    }
+    __device__ __forceinline__ void warm_out(int token, int lev, double v) const {
+        if (token >= 0 && h == 0) __stcg(warm + token + lev, v);
+    }
     __device__ __forceinline__ void issue(int s) {          // lane 0: both tiles of stage s
         const int slot = s % SC_NSTAGE;
         double* dstA = ring + slot * S2_STAGE;
@@ -390,7 +400,7 @@ scan2_solve_kernel(const ScanParams p) {
     // one block of cold state per PAIR of lanes (both run the same bookkeeping and store the same values)
     ColdState<1>& cold = *reinterpret_cast<ColdState<1>*>(sc_smem + SC_WARPS * S2_RING + SC_WARPS * SC_NSTAGE +
                                                           (size_t)(warp * scan2::NH + li) * ColdStride<1>::value);
-    ctx.parity = 0; ctx.lane = lane; ctx.h = h; ctx.N = p.N;
+    ctx.parity = 0; ctx.lane = lane; ctx.h = h; ctx.N = p.N; ctx.warm = p.warm;
     if (lane == 0) {
         for (int s = 0; s < SC_NSTAGE; ++s) mbar_init(&ctx.bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -402,7 +412,17 @@ scan2_solve_kernel(const ScanParams p) {
         if (lane == 0) item = (int)atomicAdd(p.counter, 1u);
         item = __shfl_sync(FULL, item, 0);
         if (item >= p.nitems) break;
-        const int line = item / p.groups, grp = item - line * p.groups;
+        // Items are dealt in "column" order: round r holds the lines r, R + r, 2 R + r, ... (lc of them, all their theta0
+        // groups), so that the previous LINE (line - 1: the adjacent alpha / surface of a scan grid, same theta0) was dealt
+        // one whole round >= 2 x the resident warps earlier and has normally finished: its level eigenvalues are the warm
+        // start (see the wait below).  The lines in flight
+        // at any time are ~ resident warps / groups, as in plain line order (their records stay L2-resident).
+        const int per_round = p.lc * p.groups;
+        const int rnd = item / per_round, rem = item - rnd * per_round;
+        const int jcol = rem / p.groups, grp = rem - jcol * p.groups;
+        const int line = jcol * p.rounds + rnd;
+        if (line >= p.nline) continue;
+        const int slot = line * p.groups + grp;
         const int idx = grp * scan2::NH + li;
         const bool act = idx < p.nth0;
         const size_t sidx = (size_t)line * p.nth0 + (act ? idx : p.nth0 - 1);
@@ -414,8 +434,33 @@ scan2_solve_kernel(const ScanParams p) {
         P.N = N; P.nlev = p.nlev; P.h = p.h; P.U = p.bounds[2 * line]; P.Lb = p.bounds[2 * line + 1];
         P.want_X = p.X_rows != nullptr; P.want_dX = p.dX_out != nullptr;
         ctx.line_base = p.poly + (size_t)line * p.rows_total * REC;
+        int w_in = -1, w_out = -1;
+        if (p.warm) {
+            if (rnd > 0) {            // (lanes past nth0 duplicate the last theta0: so did the same lanes of the previous line)
+                // The predecessor was dealt a whole round earlier and has normally finished; if not, wait for it: items are
+                // claimed in order, so it is already running on a resident warp and waits only on still earlier items --
+                // no deadlock -- and every line of rounds >= 1 is warm-started ALWAYS: the results do not depend on timing.
+                if (lane == 0) {
+                    const volatile unsigned* f = p.warm_flag + slot - p.groups;
+                    unsigned spins = 0;
+                    while (*f == 0u) {
+                        __nanosleep(256);
+                        if (++spins > (1u << 26)) __trap();              // a scheduling bug must trap, not hang the device
+                    }
+                }
+                __syncwarp();
+                __threadfence();
+                w_in = ((slot - p.groups) * scan2::NH + li) * scan2::WREC;
+            }
+            if (rnd + 1 < p.rounds && line + 1 < p.nline) w_out = (slot * scan2::NH + li) * scan2::WREC;
+        }
         ItemResult res;
-        scan2::solve_item2(ctx, P, th0, act, sg, p.sigma != nullptr, Xrow, dXrow, res, cold);
+        scan2::solve_item2(ctx, P, th0, act, sg, p.sigma != nullptr, Xrow, dXrow, res, cold, w_in, w_out);
+        if (w_out >= 0) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile unsigned*>(p.warm_flag + slot) = 1u;
+        }
         if (act && h == 0) {
             p.lam_out[sidx] = res.gam;
             if (p.lam_matrix_out) p.lam_matrix_out[sidx] = res.rho;
@@ -433,8 +478,8 @@ scan2_solve_kernel(const ScanParams p) {
             warp_best(bv, bi, anynan);
             unsigned prev = 0;
             if (lane == 0) {
-                p.item_val[item] = bv;
-                p.item_idx[item] = anynan ? -2 : bi;
+                p.item_val[slot] = bv;
+                p.item_idx[slot] = anynan ? -2 : bi;
                 __threadfence();
                 prev = atomicAdd(&p.surf_count[surf], 1u);
             }
@@ -619,7 +664,28 @@ static int scan_solve_lines(const SolveParams& p, int l0, int nline, int spl, bo
     auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_poly = take((size_t)nline * rows_total * REC * sizeof(double));
     const size_t o_bounds = take((size_t)nline * 2 * sizeof(double));
-    const size_t o_zero = take((2 + (size_t)nsurf) * sizeof(unsigned));             // work counters + per-surface counters: zeroed together
+    // lane-per-chain kernel: column order of the lines + warm start from the previous line (see scan2_solve_kernel); a round
+    // is at least IBS_SCAN_WARM_SPACING (default 2) x the resident warps, so that a line's predecessor has normally finished
+    int lc = nline, rounds = 1;
+    bool warm = s2;
+    if (const char* e = std::getenv("IBS_SCAN_WARM")) { if (std::atoi(e) == 0) warm = false; }
+    if ((long long)nitems * scan2::NH * scan2::WREC > 0x7fffffffLL) warm = false;           // (tokens are int element offsets)
+    if (warm) {
+        // Measured (D3D config x 37 equilibria, B200): a round of 1.0 / 1.25 / 1.5 / 2.0 / 3.0 x the resident warps -> solver
+        // 3.49 / 3.26 / 3.22 / 3.04 / 3.08 ms (no warm start: 3.47): closer rounds wait on their predecessors, wider ones
+        // leave a larger cold first round.
+        double spacing = 2.0;
+        if (const char* e = std::getenv("IBS_SCAN_WARM_SPACING")) { const double v = std::atof(e); if (v >= 1.0 && v <= 16.0) spacing = v; }
+        const long long resident = (long long)num_sms() * IBS_SCAN2_CTAS * SC_WARPS;
+        const long long lc0 = (long long)std::ceil(spacing * (double)resident / groups);       // lines per round, at least
+        rounds = (int)(nline / lc0);
+        if (rounds >= 2) lc = (nline + rounds - 1) / rounds;                                    // (>= lc0)
+        else rounds = 1;
+        if (rounds < 2) warm = false;
+    }
+    const size_t nzero = 2 + (size_t)nsurf + (warm ? (size_t)nitems : 0);
+    const size_t o_zero = take(nzero * sizeof(unsigned));             // work counters + per-surface counters + warm-start flags: zeroed together
+    const size_t o_warm = take(warm ? (size_t)nitems * scan2::NH * scan2::WREC * sizeof(double) : 0);
     const size_t o_hand = take(two ? nsolve * (sizeof(double) + sizeof(int)) : 0);
     const size_t o_ival = take(fused ? (size_t)nitems * sizeof(double) : 0);
     const size_t o_iidx = take(fused ? (size_t)nitems * sizeof(int) : 0);
@@ -633,7 +699,8 @@ static int scan_solve_lines(const SolveParams& p, int l0, int nline, int spl, bo
     sp.theta0 = p.theta0 + v0; sp.sigma = p.sigma ? p.sigma + v0 : nullptr;
     sp.nline = nline; sp.nth0 = p.nth0; sp.N = N; sp.nlev = nlev; sp.rows_total = rows_total;
     sp.groups = groups;
-    sp.nitems = nitems;
+    sp.lc = lc; sp.rounds = rounds;
+    sp.nitems = s2 ? rounds * lc * groups : nitems;          // (column order: padded; slots past nline are skipped)
     sp.h = p.h;
     sp.lam_out = p.lam_out + v0;
     sp.lam_matrix_out = p.lam_matrix_out ? p.lam_matrix_out + v0 : nullptr;
@@ -647,10 +714,12 @@ static int scan_solve_lines(const SolveParams& p, int l0, int nline, int spl, bo
     sp.lines_per_surface = fused ? p.lines_per_surface : 1;
     sp.item_val = (double*)(ws + o_ival); sp.item_idx = (int*)(ws + o_iidx);
     sp.surf_count = sp.counter + 2;
+    sp.warm = warm ? (double*)(ws + o_warm) : nullptr;
+    sp.warm_flag = warm ? sp.counter + 2 + nsurf : nullptr;
     const size_t surf0 = fused ? (size_t)l0 / p.lines_per_surface : 0;
     sp.best_out = fused ? p.best_out + 2 * surf0 : nullptr;
     sp.sigma0_out = (fused && p.sigma0_out) ? p.sigma0_out + surf0 : nullptr;
-    if (cudaError_t e = cudaMemsetAsync(sp.counter, 0, (2 + (size_t)nsurf) * sizeof(unsigned), stream); e != cudaSuccess)
+    if (cudaError_t e = cudaMemsetAsync(sp.counter, 0, nzero * sizeof(unsigned), stream); e != cudaSuccess)
         rc = cuda_fail(e, "cudaMemsetAsync(scan counters)");
     if (rc == IBS_OK) {
         scan_prep_kernel<<<nline, PREP_T, 0, stream>>>(p.base + (size_t)l0 * IBS_NBASE * N, p.dPdrho + l0, sp.theta0, p.nth0, N, p.h * p.h, nlev,

@@ -141,3 +141,52 @@ def test_lane_per_chain_code_matches_oracle_and_two_chain_code(harness):
                 np.testing.assert_allclose(B["X"][s], X * sg, rtol=0, atol=X_ATOL)
                 np.testing.assert_allclose(B["dX"][s], dX * sg, rtol=0, atol=10 * X_ATOL * max(1.0, np.max(np.abs(dX))))
     assert not lib.scan2_host_size_ok(969) and not lib.scan2_host_size_ok(1024)
+
+
+def test_lane_per_chain_warm_start_chain(harness, monkeypatch):
+    """The warm start of scan2_solve_kernel (every line starts each level from the level eigenvalues of the previous line --
+    the adjacent surface / alpha of a scan grid -- at the same theta0) must change nothing but the number of passes: lambda and
+    X agree with the cold-started solves to rounding and with the oracle to the parity tolerances.  Adjacent surfaces of the
+    tokamak case are ~1 % apart in lambda: the warm lines need far fewer passes; adjacent alphas of the stellarator case are
+    ~30 % apart: the distance guard (WARM_FAR) turns the warm start off after the first line and nothing is lost."""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    import bench
+    from oracle import ballooning_oracle as bo
+    shc, lib = harness
+    for wl, N in (("d3d", 1025), ("ncsx", 513)):
+        st, alphas, _, _ = bench.build_tables(wl, 1, 0)
+        theta = np.linspace(-4 * np.pi, 4 * np.pi, N)
+        if wl == "d3d":         # adjacent surfaces, one alpha
+            fl = bo.fieldlines(st.select(np.arange(38, 43)), np.array([0.0]), theta)
+        else:                   # one surface, adjacent alphas
+            fl = bo.fieldlines(st.select([30]), alphas[8:13], theta)
+        base = np.stack([getattr(fl, n) for n in shc.BASE_NAMES], axis=2).reshape(-1, len(shc.BASE_NAMES), N)
+        ns_, na_ = fl.bmag.shape[:2]
+        dP = np.array([bo.dpdrho_of(fl, js, ja) for js in range(ns_) for ja in range(na_)])
+        nline = base.shape[0]
+        th0 = np.tile(np.linspace(0.0, 0.5 * np.pi, 20), (nline, 1))
+        h = theta[1] - theta[0]
+        monkeypatch.setenv("IBS_SCAN_WARM", "1")
+        W = shc.host_scan_solve(lib, base, dP, th0, h, kernel="scan2")
+        monkeypatch.setenv("IBS_SCAN_WARM", "0")
+        C = shc.host_scan_solve(lib, base, dP, th0, h, kernel="scan2")
+        assert np.all((W["info"] >> 16) == 0) and np.all((C["info"] >> 16) == 0)
+        if wl == "d3d":
+            assert W["passes"] < 0.7 * C["passes"], (W["passes"], C["passes"])
+        else:
+            assert W["passes"] < 1.03 * C["passes"], (W["passes"], C["passes"])
+        np.testing.assert_allclose(W["lam"], C["lam"], rtol=1e-12)
+        # (the matrix eigenvalue is converged to ~1e-15 of the spectrum's scale U, whatever |lambda| is)
+        np.testing.assert_allclose(W["lam_matrix"], C["lam_matrix"], rtol=1e-11, atol=1e-13 * np.abs(W["bounds"][:, 0]).max())
+        np.testing.assert_allclose(W["X"], C["X"], rtol=0, atol=1e-9)
+        for (li, t) in ((1, 0), (2, 7), (4, 19), (3, 11)):
+            b = base[li]
+            cv = b[2] + th0[li, t] * b[3]
+            gd = b[4] + 2 * th0[li, t] * b[5] + th0[li, t] ** 2 * b[6]
+            info = {}
+            gam, X, dX, *_ = bo.gamma_ball_full(dP[li], theta, b[0], b[1], cv, gd, method="lambda_max", info=info)
+            sg = np.sign(X[np.argmax(np.abs(X))])
+            # (near marginal stability |lambda| << U: LAPACK itself carries ~eps U there, so the relative bar gets an absolute floor)
+            assert abs(W["lam"][li, t] - gam) <= LAM_RTOL * abs(gam) + 1e-13 * abs(W["bounds"][li, 0])
+            if info["gap"] > 1e-6:
+                np.testing.assert_allclose(W["X"][li * th0.shape[1] + t], X * sg, rtol=0, atol=X_ATOL)

@@ -22,7 +22,7 @@ def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else "d3d"
     nsurf = int(sys.argv[2]) if len(sys.argv) > 2 else 6
     st, alpha, theta0, theta = bench.build_tables(wl, 1, 0)
-    pick = np.linspace(0, st.ns - 1, nsurf).round().astype(int)
+    pick = np.arange(nsurf) + (st.ns - nsurf) // 2                      # ADJACENT surfaces: the kernel warm-starts a line from the previous one
     st = st.select(pick)
     alpha = alpha[:: max(1, alpha.size // 4)][:4]
     fl = bo.fieldlines(st, alpha, theta)
@@ -40,14 +40,20 @@ def main():
     cnt = cnt.reshape(nline, theta0.size, 8)
     nlev = lib.scan_host_num_levels(theta.size)
     print(f"{wl}: {nline} lines x {theta0.size} theta0, N = {theta.size}, levels 0..{nlev}; info iters mean {np.mean(res['info'] & 0xffff):.3f}")
+    groups = -(-theta0.size // 16)
+
+    def warp_max(c):          # warp (line, grp) holds 16 consecutive theta0
+        pad = np.concatenate([c, np.repeat(c[:, -1:], groups * 16 - theta0.size, axis=1)], axis=1)
+        return pad.reshape(nline, groups, 16).max(axis=2)
+
     tot_s = tot_w = 0.0
     for lev in range(nlev, -1, -1):
         c = cnt[:, :, lev]
-        g = c.reshape(nline, -1, 16).max(axis=2) if theta0.size % 16 == 0 else c.max(axis=1, keepdims=True)
+        g = warp_max(c)
         print(f"  level {lev} (1/{1 << lev}): per solve mean {c.mean():.3f} hist {np.bincount(c.ravel())[:10]}   per warp (max of 16) mean {g.mean():.3f} hist {np.bincount(g.ravel())[:10]}")
         tot_s += c.mean() / (1 << lev); tot_w += g.mean() / (1 << lev)
     o1 = cnt[:, :, 7]
-    g = o1.reshape(nline, -1, 16).max(axis=2) if theta0.size % 16 == 0 else o1.max(axis=1, keepdims=True)
+    g = warp_max(o1)
     print(f"  first output passes on the fine level: per solve mean {o1.mean():.3f} hist {np.bincount(o1.ravel())[:6]}, per warp mean {g.mean():.3f}")
     print(f"  fine-equivalent iteration passes: per solve {tot_s:.3f}, per warp {tot_w:.3f}")
 

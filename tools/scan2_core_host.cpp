@@ -2,6 +2,8 @@
 // a time, the two lanes of the pair (forward chain, mirrored backward chain) one after the other, with records read
 // straight from memory.  TEST INFRASTRUCTURE ONLY (tests/test_scan_core_host.py); not part of the library.
 //   g++ -O2 -std=c++17 -shared -fPIC -o scan2_core_host.so tools/scan2_core_host.cpp
+#include <cmath>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 #include "scan_core_host.cpp"        // the preparation (scan_host_prep) and the two-chains-per-lane harness
@@ -14,7 +16,10 @@ struct Host2Ctx {
     const double* line_base; int N;
     const double* lvl = nullptr; int Nl = 0; int h = 0;
     long passes = 0; double cost = 0.0;
-    int nev_lev[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // iteration passes per level (instrumentation for tools/iter_hist.py)
+    int nev_lev[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double* warm = nullptr;                              // warm-start records [2][nth0][WREC]: previous line | this line
+    double warm_in(int token, int lev) const { return (token >= 0 && lev <= MAXLEV + 1) ? warm[token + lev] : NAN; }
+    void warm_out(int token, int lev, double v) const { if (token >= 0) warm[token + lev] = v; }          // iteration passes per level (instrumentation for tools/iter_hist.py)
     void begin_pass(int lev, int Nl_, int) { lvl = line_base + (size_t)level_offset(N, lev) * REC; Nl = Nl_; }
     void wait(int) {}
     void release(int) {}
@@ -58,6 +63,7 @@ struct Host2Ctx {
     }
 };
 std::vector<int> g_counts2;
+std::vector<double> g_warm2;
 }  // namespace
 
 // iteration passes per (solve, level) of the last scan2_host_solve call: out[nsolve][8]
@@ -78,6 +84,15 @@ extern "C" long scan2_host_solve(const double* poly, const double* bounds, const
         for (int i = 0; i < nth0; ++i) {
             const size_t s = (size_t)line * nth0 + i;
             Host2Ctx ctx{poly + (size_t)line * rows_total * REC, N};
+            // the kernel's warm start: the same theta0 of the PREVIOUS line (one sweep over the lines earlier in the kernel's
+            // column order); buffer = [previous line's records | this line's records]
+            const bool use_warm = !(getenv("IBS_SCAN_WARM") && atoi(getenv("IBS_SCAN_WARM")) == 0);
+            const size_t half = (size_t)nth0 * WREC;
+            if (line == 0 && i == 0) g_warm2.assign(2 * half, NAN);
+            if (line > 0 && i == 0) { for (size_t q = 0; q < half; ++q) { g_warm2[q] = g_warm2[half + q]; g_warm2[half + q] = NAN; } }
+            ctx.warm = g_warm2.data();
+            const int w_in = (use_warm && line > 0) ? i * WREC : -1;
+            const int w_out = use_warm ? (int)half + i * WREC : -1;
             ItemProblem P;
             P.N = N; P.nlev = nlev; P.h = h; P.U = bounds[2 * line]; P.Lb = bounds[2 * line + 1];
             P.want_X = X_out != nullptr; P.want_dX = dX_out != nullptr;
@@ -85,7 +100,7 @@ extern "C" long scan2_host_solve(const double* poly, const double* bounds, const
             ItemResult res;
             ColdState<1> cold;
             solve_item2(ctx, P, theta0[s], true, sigma ? sigma[s] : 0.0, sigma != nullptr, X_out ? X_out + s * N : xscratch.data(),
-                        dX_out ? dX_out + s * N : nullptr, res, cold);
+                        dX_out ? dX_out + s * N : nullptr, res, cold, w_in, w_out);
             lam_out[s] = res.gam;
             if (lam_matrix_out) lam_matrix_out[s] = res.rho;
             if (info_out) info_out[s] = res.info;
