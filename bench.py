@@ -430,11 +430,21 @@ class Harness:
         self.barrier()
         ev = lambda: torch.cuda.Event(enable_timing=True)
         timers = [[ev() for _ in range(nstage + 1)] for _ in range(steps)]
+        # a generational collection of the interpreter in the middle of a step stalls the launches of that step for 10-100 ms
+        # (seen as one outlier step per run): collect now, not inside the timed region
+        import gc
+        gc.collect()
+        gc_was = gc.isenabled()
+        gc.disable()
         t_wall = time.perf_counter()
-        for k in range(steps):
-            step(timers[k])
-            self.flush.zero_()                  # L2 flush between timed iterations (outside the event brackets)
-        self.barrier()
+        try:
+            for k in range(steps):
+                step(timers[k])
+                self.flush.zero_()              # L2 flush between timed iterations (outside the event brackets)
+            self.barrier()
+        finally:
+            if gc_was:
+                gc.enable()
         wall = time.perf_counter() - t_wall
         stage = np.array([[t[i].elapsed_time(t[i + 1]) for i in range(nstage)] for t in timers])
         total = np.array([t[0].elapsed_time(t[nstage]) for t in timers])

@@ -378,8 +378,7 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
     keep_pool_cached();
     // Three streams: uploads, compute, downloads.  The surfaces are processed in chunks (every chunk: tables up ->
     // K1 -> K2+K3 -> arg-max -> eigenfunction of each surface's maximum -> results down), so that the copies of one chunk
-    // overlap the kernels of its neighbours; a chunk keeps >= 4 rounds of the solver's resident warps busy (measured on
-    // the D3D config x 37 equilibria: 1 / 2 / 4 chunks = 3.37e7 / 3.55e7 / 3.22e7 solves/s; IBS_HOST_CHUNKS overrides).
+    // overlap the kernels of its neighbours (chunk boundaries cb[] below).
     // Streams and events are created once per device and reused (the call holds the device's context lock).
     HostCtx& hc = host_ctx();
     std::lock_guard<std::mutex> hold(hc.mu);
@@ -387,15 +386,22 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
     cudaStream_t st_h = hc.st_h, st = hc.st, st_d = hc.st_d;
     const size_t nlines = (size_t)ns * nalpha, nsolve = nlines * nth0;
     const int ngrid = nalpha * nth0;
-    int nchunk = 1;
+    // Equal chunks of >= 4 rounds of the lane kernel's resident warps each.  Measured on the D3D config x 37 equilibria:
+    // 1 / 2 / 3 / 4 / 6 chunks = 5.3e7 / 6.4e7 / 5.6e7 / 5.5e7 / 5.0e7 solves/s; SMALL first and last chunks (the only copies
+    // nothing overlaps) with one large chunk between them: 6.0e7 -- what they save in exposed copies they lose in the
+    // solver (a short chunk is one cold round).  IBS_HOST_CHUNKS overrides.
+    std::vector<size_t> cb;
     {
-        const long long items = (long long)nlines * ((nth0 + 31) / 32), per_round = 8LL * num_sms();
-        nchunk = (int)(items / (4 * per_round));
-        if (const char* e = std::getenv("IBS_HOST_CHUNKS")) nchunk = std::atoi(e);
-        if (nchunk > MAX_HOST_CHUNKS) nchunk = MAX_HOST_CHUNKS;
-        if (nchunk > ns) nchunk = ns;
-        if (nchunk < 1) nchunk = 1;
+        const int grp = (nth0 + 15) / 16;
+        const long long items = (long long)nlines * grp, per_round = 16LL * num_sms();
+        int n = (int)(items / (4 * per_round));
+        if (const char* e = std::getenv("IBS_HOST_CHUNKS")) n = std::atoi(e);
+        if (n > MAX_HOST_CHUNKS) n = MAX_HOST_CHUNKS;
+        if (n > ns) n = ns;
+        if (n < 1) n = 1;
+        for (int c = 0; c <= n; ++c) cb.push_back((size_t)ns * c / n);
     }
+    const int nchunk = (int)cb.size() - 1;
     const size_t r_mn = (size_t)6 * mnmax * 8, r_nyq = (size_t)7 * mnmax_nyq * 8, r_sc = (size_t)IBS_NSCAL * 8;      // bytes per surface
     // one device arena: inputs | base | dPdrho | theta0 per solve | gamma | val | sigma0 | idx | info | best-solve scratch
     size_t off = 0;
@@ -425,7 +431,7 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
     IBS_TRY(cudaGetLastError());
     IBS_TRY(cudaMemsetAsync(d + o_nb, 0, 4, st_h));
     for (int c = 0; c < nchunk; ++c) {
-        const size_t s0 = (size_t)ns * c / nchunk, nsc = (size_t)ns * (c + 1) / nchunk - s0;
+        const size_t s0 = cb[c], nsc = cb[c + 1] - s0;
         IBS_TRY(cudaMemcpyAsync(d + o_tmn + s0 * r_mn, (const char*)tab_mn + s0 * r_mn, nsc * r_mn, cudaMemcpyHostToDevice, st_h));
         IBS_TRY(cudaMemcpyAsync(d + o_tnq + s0 * r_nyq, (const char*)tab_nyq + s0 * r_nyq, nsc * r_nyq, cudaMemcpyHostToDevice, st_h));
         IBS_TRY(cudaMemcpyAsync(d + o_sc + s0 * r_sc, (const char*)scal + s0 * r_sc, nsc * r_sc, cudaMemcpyHostToDevice, st_h));
@@ -433,7 +439,7 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
     }
     // ---- compute + downloads, chunk by chunk
     for (int c = 0; c < nchunk; ++c) {
-        const size_t s0 = (size_t)ns * c / nchunk, nsc = (size_t)ns * (c + 1) / nchunk - s0;
+        const size_t s0 = cb[c], nsc = cb[c + 1] - s0;
         const size_t l0 = s0 * nalpha, nlc = nsc * nalpha, v0 = l0 * nth0, nvc = nlc * nth0;
         double* base_c = (double*)(d + o_base) + l0 * IBS_NBASE * nl;
         double* dp_c = (double*)(d + o_dp) + l0;

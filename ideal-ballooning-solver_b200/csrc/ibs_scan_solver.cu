@@ -272,6 +272,9 @@ scan_solve_kernel(const ScanParams p) {
 #ifndef IBS_SCAN2_CTAS
 #define IBS_SCAN2_CTAS 4          // CTAs of 4 warps per SM the kernel is compiled for (register cap 65536 / (128 * CTAS))
 #endif
+#ifndef IBS_SCAN2_PREFETCH_K
+#define IBS_SCAN2_PREFETCH_K 0      // measured: 3.09 vs 3.03 ms with the prefetch (the L1 line rarely survives until the join)
+#endif
 constexpr int S2_TILE = scan2::T0 * REC;           // doubles per tile (35 records)
 constexpr int S2_STAGE = 2 * S2_TILE;              // ascending tile (forward lanes) + descending tile (backward lanes)
 constexpr int S2_RING = SC_NSTAGE * S2_STAGE;      // doubles per warp (10 KB with 3 stages)
@@ -334,6 +337,15 @@ struct Dev2Ctx {
     }
     __device__ __forceinline__ double xd(double v) const { return __shfl_xor_sync(FULL, v, 16); }
     __device__ __forceinline__ int xi(int v) const { return __shfl_xor_sync(FULL, v, 16); }
+    // the join of a pass reads the record of the matching row from global memory: ask for it when the pass starts, so that the
+    // L2 round trip is over by then (it is ~20 % of the issue time of a pass on the coarsest level)
+    __device__ __forceinline__ void prefetch_k(int lev, int k) const {
+#if IBS_SCAN2_PREFETCH_K
+        const double* q = line_base + ((size_t)level_offset(N, lev) + k) * REC;
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(q));
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(q + REC - 1));       // (a 48-byte record may straddle two 32-byte sectors' lines)
+#endif
+    }
     __device__ __forceinline__ Rec rec_k(int k) const {        // record of the matching row (global memory; L2)
         const double2* q = reinterpret_cast<const double2*>(lvl + (size_t)k * REC);
         const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
@@ -343,6 +355,7 @@ struct Dev2Ctx {
     // ---- the passes of solve_item2: my chain, the partner's end state by shuffle, the join
     __device__ __forceinline__ void eval(int lev, int Nl_, int k, double th0, double lam, double& r, double& S, int& nodes) {
         const int qf = k, qb = Nl_ - 1 - k;
+        prefetch_k(lev, k);
         const scan2::EvalEnd me = scan2::eval_lane(*this, lev, Nl_, h ? qb : qf, qf > qb ? qf : qb, th0, lam);
         scan2::EvalEnd ot;
         ot.X = xd(me.X); ot.W = xd(me.W); ot.S = xd(me.S); ot.nodes = xi(me.nodes);
@@ -350,6 +363,7 @@ struct Dev2Ctx {
     }
     __device__ __forceinline__ void out1(int lev, int Nl_, int k, double th0, double lam, SolveOut& out) {
         const int qf = k, qb = Nl_ - 1 - k;
+        prefetch_k(lev, k);
         const Sweep me = scan2::out_lane<false>(*this, lev, Nl_, h ? qb : qf, qf > qb ? qf : qb, h != 0, th0, lam, 0.0, 0, nullptr);
         Sweep ot;
         ot.x = xd(me.x); ot.w = xd(me.w); ot.E = xi(me.E); ot.W2 = xd(me.W2); ot.W3 = xd(me.W3); ot.W4 = xd(me.W4); ot.gp = xd(me.gp); ot.gpp = xd(me.gpp);

@@ -5,5 +5,5 @@ cd "$(dirname "$0")/../ideal-ballooning-solver_b200"
 mkdir -p lib/variants
 F="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -DIBS_BUILD -fmad=true"
 nvcc $F $2 -Xptxas=-v -c csrc/ibs_geometry.cu -o lib/variants/geo_$1.o 2> lib/variants/ptxas_geo_$1.log
-nvcc -shared -o lib/variants/libibs_$1.so lib/ibs_api.o lib/ibs_solver.o lib/ibs_scan_solver.o lib/variants/geo_$1.o lib/ibs_geometry_full.o lib/ibs_adjoint.o -gencode arch=compute_100a,code=sm_100a -cudart static
+nvcc -shared -o lib/variants/libibs_$1.so lib/ibs_api.o lib/ibs_solver.o lib/ibs_scan_solver.o lib/variants/geo_$1.o lib/ibs_geometry_full.o lib/ibs_geometry_adjoint.o lib/ibs_adjoint.o -gencode arch=compute_100a,code=sm_100a -cudart static
 grep -A2 "geometry_kernelILi11ELi13" lib/variants/ptxas_geo_$1.log | tail -2
