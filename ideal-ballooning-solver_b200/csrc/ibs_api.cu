@@ -106,7 +106,7 @@ __global__ void count_bad_kernel(const int* __restrict__ info, long long n, int*
 }
 
 // Streams and events of ibs_scan_host, created once per device and reused by every call.
-constexpr int MAX_HOST_CHUNKS = 8;
+constexpr int MAX_HOST_CHUNKS = 8, MAX_HOST_SUBCHUNKS = 8;
 struct HostCtx {
     std::mutex mu;
     cudaStream_t st_h = nullptr, st = nullptr, st_d = nullptr;
@@ -382,26 +382,43 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
     // Streams and events are created once per device and reused (the call holds the device's context lock).
     HostCtx& hc = host_ctx();
     std::lock_guard<std::mutex> hold(hc.mu);
-    if (int rc0 = hc.ensure(MAX_HOST_CHUNKS)) return rc0;
+    if (int rc0 = hc.ensure(MAX_HOST_CHUNKS * (MAX_HOST_SUBCHUNKS + 1))) return rc0;
     cudaStream_t st_h = hc.st_h, st = hc.st, st_d = hc.st_d;
     const size_t nlines = (size_t)ns * nalpha, nsolve = nlines * nth0;
     const int ngrid = nalpha * nth0;
-    // Equal chunks of >= 4 rounds of the lane kernel's resident warps each.  Measured on the D3D config x 37 equilibria:
-    // 1 / 2 / 3 / 4 / 6 chunks = 5.3e7 / 6.4e7 / 5.6e7 / 5.5e7 / 5.0e7 solves/s; SMALL first and last chunks (the only copies
-    // nothing overlaps) with one large chunk between them: 6.0e7 -- what they save in exposed copies they lose in the
-    // solver (a short chunk is one cold round).  IBS_HOST_CHUNKS overrides.
+    // Chunks of >= 8 rounds of the lane kernel's resident warps (ONE solver launch per chunk: the lane kernel warm-starts
+    // every line after its first two rounds, so short launches are slow launches), each cut into NSUB sub-chunks for the
+    // copies: tables of sub-chunk i+1 go up while K1 runs on sub-chunk i, the eigenfunctions of sub-chunk i go down while
+    // those of i+1 are re-solved.  Only 1/NSUB of the first upload and of the last download overlap nothing.
+    // Measured, D3D config x 37 equilibria (solves/s): equal chunks with their own solver launch 1 / 2 / 3 / 4 / 6 =
+    // 5.3e7 / 6.4e7 / 5.6e7 / 5.5e7 / 5.0e7; small first / last chunks 6.0e7; this form with 1 / 2 / 4 / 8 sub-chunks:
+    // 6.1e7 / 6.9e7 / 7.2e7 / 7.1e7.
+    // IBS_HOST_CHUNKS / IBS_HOST_SUBCHUNKS override.
     std::vector<size_t> cb;
+    int nsub = 4;
     {
         const int grp = (nth0 + 15) / 16;
         const long long items = (long long)nlines * grp, per_round = 16LL * num_sms();
-        int n = (int)(items / (4 * per_round));
+        int n = (int)(items / (8 * per_round));
         if (const char* e = std::getenv("IBS_HOST_CHUNKS")) n = std::atoi(e);
         if (n > MAX_HOST_CHUNKS) n = MAX_HOST_CHUNKS;
         if (n > ns) n = ns;
         if (n < 1) n = 1;
         for (int c = 0; c <= n; ++c) cb.push_back((size_t)ns * c / n);
+        {   // sub-chunks pay only when a chunk's copies are large (>= 4 MB each); small ones cost K1 its full-size launches
+            const size_t per_surface = (size_t)(6 * mnmax + 7 * mnmax_nyq + IBS_NSCAL) * 8;
+            const size_t up = per_surface * (size_t)ns / n, down = xbest_out ? (size_t)nl * 8 * (size_t)ns / n : 0;
+            const size_t big = up > down ? up : down;
+            nsub = (int)(big / ((size_t)4 << 20));
+            if (nsub > 4) nsub = 4;
+        }
+        if (const char* e = std::getenv("IBS_HOST_SUBCHUNKS")) nsub = std::atoi(e);
+        if (nsub > MAX_HOST_SUBCHUNKS) nsub = MAX_HOST_SUBCHUNKS;
+        if ((size_t)nsub > (size_t)ns / n) nsub = (int)((size_t)ns / n);
+        if (nsub < 1) nsub = 1;
     }
     const int nchunk = (int)cb.size() - 1;
+    auto sub_lo = [&](int c, int q) { return cb[c] + (cb[c + 1] - cb[c]) * (size_t)q / (size_t)nsub; };      // first surface of sub-chunk q of chunk c
     const size_t r_mn = (size_t)6 * mnmax * 8, r_nyq = (size_t)7 * mnmax_nyq * 8, r_sc = (size_t)IBS_NSCAL * 8;      // bytes per surface
     // one device arena: inputs | base | dPdrho | theta0 per solve | gamma | val | sigma0 | idx | info | best-solve scratch
     size_t off = 0;
@@ -430,24 +447,30 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
     replicate_theta0_kernel<<<(unsigned)((nsolve + 255) / 256), 256, 0, st_h>>>((double*)(d + o_t0h), nth0, (long long)nsolve, (double*)(d + o_t0));
     IBS_TRY(cudaGetLastError());
     IBS_TRY(cudaMemsetAsync(d + o_nb, 0, 4, st_h));
-    for (int c = 0; c < nchunk; ++c) {
-        const size_t s0 = cb[c], nsc = cb[c + 1] - s0;
-        IBS_TRY(cudaMemcpyAsync(d + o_tmn + s0 * r_mn, (const char*)tab_mn + s0 * r_mn, nsc * r_mn, cudaMemcpyHostToDevice, st_h));
-        IBS_TRY(cudaMemcpyAsync(d + o_tnq + s0 * r_nyq, (const char*)tab_nyq + s0 * r_nyq, nsc * r_nyq, cudaMemcpyHostToDevice, st_h));
-        IBS_TRY(cudaMemcpyAsync(d + o_sc + s0 * r_sc, (const char*)scal + s0 * r_sc, nsc * r_sc, cudaMemcpyHostToDevice, st_h));
-        IBS_TRY(cudaEventRecord(ev_h[c], st_h));
-    }
+    for (int c = 0; c < nchunk; ++c)
+        for (int q = 0; q < nsub; ++q) {
+            const size_t s0 = sub_lo(c, q), nsc = sub_lo(c, q + 1) - s0;
+            IBS_TRY(cudaMemcpyAsync(d + o_tmn + s0 * r_mn, (const char*)tab_mn + s0 * r_mn, nsc * r_mn, cudaMemcpyHostToDevice, st_h));
+            IBS_TRY(cudaMemcpyAsync(d + o_tnq + s0 * r_nyq, (const char*)tab_nyq + s0 * r_nyq, nsc * r_nyq, cudaMemcpyHostToDevice, st_h));
+            IBS_TRY(cudaMemcpyAsync(d + o_sc + s0 * r_sc, (const char*)scal + s0 * r_sc, nsc * r_sc, cudaMemcpyHostToDevice, st_h));
+            IBS_TRY(cudaEventRecord(ev_h[c * nsub + q], st_h));
+        }
     // ---- compute + downloads, chunk by chunk
     for (int c = 0; c < nchunk; ++c) {
         const size_t s0 = cb[c], nsc = cb[c + 1] - s0;
         const size_t l0 = s0 * nalpha, nlc = nsc * nalpha, v0 = l0 * nth0, nvc = nlc * nth0;
         double* base_c = (double*)(d + o_base) + l0 * IBS_NBASE * nl;
         double* dp_c = (double*)(d + o_dp) + l0;
-        IBS_TRY(cudaStreamWaitEvent(st, ev_h[c], 0));
-        rc = geometry_dispatch((double*)(d + o_tmn + s0 * r_mn), (double*)(d + o_tnq + s0 * r_nyq), (double*)(d + o_sc + s0 * r_sc), xm, xn,
-                               xm_nyq, xn_nyq, (int)nsc, mnmax, mnmax_nyq, phiedge, aminor_p, (double*)(d + o_al), nalpha, 0,
-                               (double*)(d + o_th), nl, 0.0, base_c, dp_c, nullptr, nullptr, st);
-        if (rc != IBS_OK) goto done;
+        // K1, sub-chunk by sub-chunk as the tables arrive
+        for (int q = 0; q < nsub; ++q) {
+            const size_t q0 = sub_lo(c, q), nq = sub_lo(c, q + 1) - q0;
+            IBS_TRY(cudaStreamWaitEvent(st, ev_h[c * nsub + q], 0));
+            rc = geometry_dispatch((double*)(d + o_tmn + q0 * r_mn), (double*)(d + o_tnq + q0 * r_nyq), (double*)(d + o_sc + q0 * r_sc), xm, xn,
+                                   xm_nyq, xn_nyq, (int)nq, mnmax, mnmax_nyq, phiedge, aminor_p, (double*)(d + o_al), nalpha, 0,
+                                   (double*)(d + o_th), nl, 0.0, (double*)(d + o_base) + q0 * nalpha * IBS_NBASE * nl,
+                                   (double*)(d + o_dp) + q0 * nalpha, nullptr, nullptr, st);
+            if (rc != IBS_OK) goto done;
+        }
         {
             // K2+K3 with the per-surface arg-max fused into the solver's epilogue (one packed (max, index) pair per surface)
             SolveParams p = blank_params();
@@ -465,29 +488,37 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
         rc = launch_best_setup((double*)(d + o_best) + 2 * s0, (double*)(d + o_t0) + v0, (int)nsc, ngrid, nth0, (double*)(d + o_val) + s0,
                                (int*)(d + o_idx) + s0, (int*)(d + o_bl) + s0, (double*)(d + o_bt) + s0, st);
         if (rc != IBS_OK) goto done;
-        if (xbest_out && !xall_out) {
-            // eigenfunction of each surface's arg-max only: re-solve those problems with the eigenvector written out
-            // (instead of writing nsolve eigenvectors and gathering ns of them)
-            SolveParams pb = blank_params();
-            pb.base = base_c; pb.dPdrho = dp_c; pb.theta0 = (double*)(d + o_bt) + s0;
-            pb.line_of_solve = (int*)(d + o_bl) + s0; pb.nth0 = 1; pb.nsolve = (int)nsc; pb.N = nl; pb.h = h;
-            pb.lam_out = (double*)(d + o_bg) + s0; pb.X_out = (double*)(d + o_xb) + s0 * nl;
-            rc = solve_dispatch(pb, true, false, st);
-            if (rc != IBS_OK) goto done;
-        } else if (xbest_out) {
-            rc = launch_gather_best((double*)(d + o_xa) + v0 * nl, (int*)(d + o_idx) + s0, (int)nsc, ngrid, nl, (double*)(d + o_xb) + s0 * nl, st);
-            if (rc != IBS_OK) goto done;
-        }
         count_bad_kernel<<<(unsigned)((nvc + 255) / 256), 256, 0, st>>>((int*)(d + o_info) + v0, (long long)nvc, (int*)(d + o_nb));
         IBS_TRY(cudaGetLastError());
-        IBS_TRY(cudaEventRecord(ev_c[c], st));
-        IBS_TRY(cudaStreamWaitEvent(st_d, ev_c[c], 0));
+        // the grid results go down while the eigenfunctions are formed
+        IBS_TRY(cudaEventRecord(ev_c[c * (nsub + 1)], st));
+        IBS_TRY(cudaStreamWaitEvent(st_d, ev_c[c * (nsub + 1)], 0));
         IBS_TRY(cudaMemcpyAsync(gamma_out + v0, d + o_gam + v0 * 8, nvc * 8, cudaMemcpyDeviceToHost, st_d));
         if (val_out) IBS_TRY(cudaMemcpyAsync(val_out + s0, d + o_val + s0 * 8, nsc * 8, cudaMemcpyDeviceToHost, st_d));
         if (idx_out) IBS_TRY(cudaMemcpyAsync(idx_out + s0, d + o_idx + s0 * 4, nsc * 4, cudaMemcpyDeviceToHost, st_d));
         if (sigma0_out) IBS_TRY(cudaMemcpyAsync(sigma0_out + s0, d + o_sig + s0 * 8, nsc * 8, cudaMemcpyDeviceToHost, st_d));
-        if (xbest_out) IBS_TRY(cudaMemcpyAsync(xbest_out + s0 * nl, d + o_xb + s0 * nl * 8, nsc * nl * 8, cudaMemcpyDeviceToHost, st_d));
-        if (xall_out) IBS_TRY(cudaMemcpyAsync(xall_out + v0 * nl, d + o_xa + v0 * nl * 8, nvc * nl * 8, cudaMemcpyDeviceToHost, st_d));
+        for (int q = 0; q < nsub && (xbest_out || xall_out); ++q) {
+            const size_t q0 = sub_lo(c, q), nq = sub_lo(c, q + 1) - q0;
+            const size_t qv0 = q0 * nalpha * nth0, nqv = nq * nalpha * nth0;
+            if (xbest_out && !xall_out) {
+                // eigenfunction of each surface's arg-max only: re-solve those problems with the eigenvector written out
+                // (instead of writing nsolve eigenvectors and gathering ns of them); line indices are chunk-local
+                SolveParams pb = blank_params();
+                pb.base = base_c; pb.dPdrho = dp_c; pb.theta0 = (double*)(d + o_bt) + q0;
+                pb.line_of_solve = (int*)(d + o_bl) + q0; pb.nth0 = 1; pb.nsolve = (int)nq; pb.N = nl; pb.h = h;
+                pb.lam_out = (double*)(d + o_bg) + q0; pb.X_out = (double*)(d + o_xb) + q0 * nl;
+                rc = solve_dispatch(pb, true, false, st);
+                if (rc != IBS_OK) goto done;
+            } else if (xbest_out) {
+                // idx is local to the surface; the gather kernel takes this sub-chunk's first solve as its base
+                rc = launch_gather_best((double*)(d + o_xa) + qv0 * nl, (int*)(d + o_idx) + q0, (int)nq, ngrid, nl, (double*)(d + o_xb) + q0 * nl, st);
+                if (rc != IBS_OK) goto done;
+            }
+            IBS_TRY(cudaEventRecord(ev_c[c * (nsub + 1) + 1 + q], st));
+            IBS_TRY(cudaStreamWaitEvent(st_d, ev_c[c * (nsub + 1) + 1 + q], 0));
+            if (xbest_out) IBS_TRY(cudaMemcpyAsync(xbest_out + q0 * nl, d + o_xb + q0 * nl * 8, nq * nl * 8, cudaMemcpyDeviceToHost, st_d));
+            if (xall_out) IBS_TRY(cudaMemcpyAsync(xall_out + qv0 * nl, d + o_xa + qv0 * nl * 8, nqv * nl * 8, cudaMemcpyDeviceToHost, st_d));
+        }
     }
     IBS_TRY(cudaMemcpyAsync(&nbad_host, d + o_nb, 4, cudaMemcpyDeviceToHost, st_d));
     IBS_TRY(cudaEventRecord(ev_done, st_d));
