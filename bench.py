@@ -174,6 +174,17 @@ class ClockSampler:
                                        "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+        # nvidia-smi's start-up (driver handshake, first query) stalls the device for tens of ms: let it finish BEFORE the
+        # warm-up starts, i.e. wait for its first sample (its steady-state queries do not perturb the steps: checked with
+        # IBS_BENCH_NO_SAMPLER=1)
+        t0 = time.perf_counter()
+        while self.p is not None and self.p.poll() is None and time.perf_counter() - t0 < 3.0:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    break
+            except OSError:
+                break
+            time.sleep(0.02)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -424,20 +435,21 @@ class Harness:
         # the clock sampler starts BEFORE the warm-up (nvidia-smi's start-up stalls the device for a few ms)
         if sample_clocks and self.rank == 0 and self.sampler is None:
             self.sampler = ClockSampler(torch.cuda.current_device())
-        for _ in range(warmup):
-            step(None)
-            self.flush.zero_()
-        self.barrier()
+        # Everything that is not a step happens BEFORE the warm-up -- event creation, a generational collection of the
+        # interpreter (10-100 ms when it strikes inside a step) -- so that the warm-up runs straight into the timed steps: an
+        # idle gap of a few ms between them lets the clocks drop, and the first timed step then took 4-80 ms instead of 3.6.
         ev = lambda: torch.cuda.Event(enable_timing=True)
         timers = [[ev() for _ in range(nstage + 1)] for _ in range(steps)]
-        # a generational collection of the interpreter in the middle of a step stalls the launches of that step for 10-100 ms
-        # (seen as one outlier step per run): collect now, not inside the timed region
         import gc
         gc.collect()
         gc_was = gc.isenabled()
         gc.disable()
-        t_wall = time.perf_counter()
         try:
+            for _ in range(warmup):
+                step(None)
+                self.flush.zero_()
+            self.barrier()
+            t_wall = time.perf_counter()
             for k in range(steps):
                 step(timers[k])
                 self.flush.zero_()              # L2 flush between timed iterations (outside the event brackets)
@@ -448,6 +460,9 @@ class Harness:
         wall = time.perf_counter() - t_wall
         stage = np.array([[t[i].elapsed_time(t[i + 1]) for i in range(nstage)] for t in timers])
         total = np.array([t[0].elapsed_time(t[nstage]) for t in timers])
+        if os.environ.get("IBS_BENCH_DUMP_STEPS"):       # diagnostic: which steps are the slow ones, and in which stage
+            big = np.argsort(total)[-3:][::-1]
+            print("slowest steps:", [(int(k), round(float(total[k]), 3), [round(float(x), 3) for x in stage[k]]) for k in big], file=sys.stderr)
         return self.max_over_ranks(total.sum()) * 1e-3, stage, total, wall
 
     def clocks(self):

@@ -33,6 +33,9 @@ constexpr int NH = 16;            // solves per warp
 constexpr int T0 = TR + 3;        // records of stage 0: steps 0 .. 34
 constexpr int NPRE = 5;           // steps 0 .. 4 are done one at a time (start values, the end-point stencils); chunks start at step 5
 constexpr int KQ = 16;            // chain ends (and chunk ends) are multiples of KQ
+#ifndef IBS_SCAN2_EXTRAP
+#define IBS_SCAN2_EXTRAP 1
+#endif
 constexpr int WREC = MAXLEV + 2;  // warm-start record: the eigenvalue of every level (index = level) + how far the neighbour was
 constexpr double WARM_FAR = 0.05; // relative distance of the coarsest-level eigenvalues beyond which a neighbour is no help
 
@@ -361,11 +364,24 @@ IBS_HD void solve_item2(Ctx& ctx, const ItemProblem& P, double th0, bool act, do
                 iter_update(it, r, S, nodes, P.U, fine ? tol : tol_lvl, tol_stag, fine ? tol : 1e-7 * scale, true);
                 // Each pass restarts from e_k, so the error obeys e' = C e^2 with C a property of the spectrum and of the
                 // matching row (about the same on every level): two consecutive in-basin corrections measure it ...
-                if (nodes == 0 && dp0 < 1e-2 * scale && it.dprev < 0.1 * dp0 && it.dprev > 0.0) Cq = it.dprev / (dp0 * dp0);
+                // (e0 = d0 + e1, e1 = C e0^2 ~ d1: C = d1 / (d0 + d1)^2)
+                if (nodes == 0 && dp0 < 1e-2 * scale && it.dprev < 0.7 * dp0 && it.dprev > 0.0) {
+                    const double e0 = dp0 + it.dprev;
+                    Cq = it.dprev / (e0 * e0);
+                }
                 // ... and on the next levels ONE pass is enough when the error it leaves, C dl^2, is predicted (x 10) below
                 // what the extrapolation to the finer level can use
                 if (!it.done && !fine && it.rq && Cq > 0.0 && 10.0 * Cq * it.dprev * it.dprev <= tol_lvl) { it.done = true; it.conv = true; }
             }
+#if IBS_SCAN2_EXTRAP
+            // ... and what the step just taken leaves, C dl^2 (the Rayleigh quotient is below lam_max from either side), is
+            // added to it: one order of convergence more per pass in the slow phase (C dl ~ 0.1 - 0.5) of a cold start.  An
+            // overshoot lands just above lam_max, where the next pass is a full step again.
+            if (!it.done && it.rq && Cq > 0.0) {
+                const double x = Cq * it.dprev;
+                if (x < 0.25) it.lam = fmin(it.lam + x * it.dprev / (1.0 - 2.0 * x), 0.5 * (it.lam + it.hi));
+            }
+#endif
             sh = it.lam;
             // Fine level: after an in-basin step whose successor is predicted tiny (q = C dl), go straight to the first output
             // pass at lam + dl -- it IS an iteration pass (out_join returns its correction) and confirms or rejects the step

@@ -260,4 +260,4 @@ def test_lane_per_chain_warm_start_is_deterministic_and_changes_nothing(cuda_lib
     assert float(same.double().mean().item()) > 0.99
     assert float(((best_a[:, 0] - best_c[:, 0]).abs() / best_c[:, 0].abs().clamp_min(1e-6)).max().item()) < 1e-10
     it_w = float((a.info & 0xFFFF).double().mean().item()); it_c = float((c.info & 0xFFFF).double().mean().item())
-    assert it_w < 0.9 * it_c, (it_w, it_c)
+    assert it_w < 0.95 * it_c, (it_w, it_c)           # (2560 lines = two rounds: half of them warm)
