@@ -414,6 +414,7 @@ class Harness:
         _lib.load(build_if_missing=True)
         self.flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=self.dev)     # > 126 MB L2
         self.sampler = None
+        self.is_last = False
 
     def barrier(self):
         if self.world > 1:
@@ -451,8 +452,10 @@ class Harness:
             self.barrier()
             t_wall = time.perf_counter()
             for k in range(steps):
+                self.is_last = k == steps - 1
                 step(timers[k])
                 self.flush.zero_()              # L2 flush between timed iterations (outside the event brackets)
+            self.is_last = False
             self.barrier()
         finally:
             if gc_was:
@@ -515,18 +518,32 @@ def run_scan(H, args):
                     h=engine.grid_spacing(theta), dt=engine.DeviceTables.from_host(st, dev),
                     alpha_d=torch.from_numpy(alpha).to(dev), theta_d=torch.from_numpy(theta).to(dev),
                     th0_d=torch.from_numpy(theta0).to(dev).repeat(ns * na), nsolve=ns * na * nt, nlines=ns * na)
-        case["gather"] = scan.SurfaceGather(case["ns_total"], dev)
+        # two exchange buffers used alternately: the all-gather of step k overlaps the kernels of step k + 1 (N > 1)
+        case["gathers"] = [scan.SurfaceGather(case["ns_total"], dev) for _ in range(2 if world > 1 else 1)]
+        case["gather"] = case["gathers"][0]
+        case["nstep"] = 0
         return case
 
     def make_step(case):
         def step(t):
+            gs = case["gathers"]
+            g, g_prev = gs[case["nstep"] % len(gs)], gs[(case["nstep"] + 1) % len(gs)]
+            case["nstep"] += 1
             rec(t, 0)
             geo = engine.geometry_batch(case["dt"], case["alpha_d"], case["theta_d"])
             rec(t, 1)
+            g.wait()                             # (its exchange of two steps ago: long done)
             sol, best, sig = engine.scan_solve_argmax(geo.base, geo.dPdrho, case["th0_d"], case["h"], nt, na, want_X=True,
-                                                      chain_len=chain, best_out=case["gather"].send)
+                                                      chain_len=chain, best_out=g.send)
             rec(t, 2)
-            case["gather"].exchange()            # N > 1: one all_gather_into_tensor of the packed (max, index) pairs
+            # N > 1: one all_gather_into_tensor of the packed (max, index) pairs, enqueued behind the solver and left to overlap
+            # the next step's kernels; every step waits for the PREVIOUS step's exchange, the last timed step for its own too,
+            # so all K exchanges complete inside the K timed brackets
+            g.exchange(async_op=len(gs) > 1)
+            if len(gs) > 1:
+                g_prev.wait()
+                if H.is_last:
+                    g.wait()
             rec(t, 3)
             return sol
         return step
@@ -606,7 +623,10 @@ def run_scan(H, args):
     fma_solver = rows * ((13.0 * mean_iters + 38.0) if scan_eligible(nt, N) else (22.0 * mean_iters + 40.0))
     fma_geo = (10.0 * len(st.xm) + 9.0 * len(st.xm_nyq)) * N * main_case["nlines"]
     rf64 = fp64_rooflines(H, [(kname, fma_solver, solve_ms, "FMAs per solve = N x (13 x evaluations + 38) [lane kernel] or N x (22 x evaluations + 40) [team kernel]; kernel_ms includes the coefficient prep"),
-                              ("geometry_kernel (K1)", fma_geo, float(t_geo.mean()), "algorithmic FMAs per point = 10 mnmax + 9 mnmax_nyq (SURVEY 8d); Newton and pointwise algebra not counted")])
+                              ("geometry_kernel (K1)", fma_geo, float(t_geo.mean()), "algorithmic FMAs per point = 10 mnmax + 9 mnmax_nyq (SURVEY 8d); Newton and pointwise algebra not counted" +
+                               ("; axisymmetric tables on a 2 pi-periodic theta grid: points one poloidal turn apart share their mode sums "
+                                "(periodicity fold), so the EXECUTED mode-sum FMAs are ~1/%d of this algorithmic count" % max(1, int(round(span)))
+                                if kind == "d3d" else ""))])
     launches = 6      # pack_mn, pack_nyq, geometry, dpdrho + (scan_prep, scan_solve [arg-max fused] | solve, argmax)
     line = {
         "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -617,7 +637,8 @@ def run_scan(H, args):
                    "eigvec": "X written to HBM for every solve",
                    "mean_solver_iterations": mean_iters,      # fine-grid-equivalent evaluations per solve (output passes not counted)
                    "solver": kname, "argmax": "fused into the solver kernel's epilogue" if scan_eligible(nt, N) else "argmax_kernel",
-                   "collective": "one all_gather_into_tensor of the packed per-surface (max, index) pairs" if world > 1 else "none (1 GPU)",
+                   "collective": ("one all_gather_into_tensor of the packed per-surface (max, index) pairs per step, asynchronous: it overlaps the next "
+                                  "step's kernels (two buffers); all K exchanges complete inside the K timed brackets") if world > 1 else "none (1 GPU)",
                    "theta0_chain": chain, "bad_solves": nbad},
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None if tps is None else tps * main_case["nsolve"], "peak_source": peak_src,

@@ -33,6 +33,9 @@ constexpr int GEO_THREADS = 128;          // axisymmetric tables: 128-point tile
 #ifndef IBS_GEO_THREADS_3D
 #define IBS_GEO_THREADS_3D 128
 #endif
+#ifndef IBS_GEO_NROWS_DERIVED
+#define IBS_GEO_NROWS_DERIVED 1
+#endif
 #ifndef IBS_GEO_SMEM_NEWTON
 #define IBS_GEO_SMEM_NEWTON 0
 #endif
@@ -341,6 +344,29 @@ geometry_kernel(const GeoParams p) {
                     double A[9], Bv[9];
 #pragma unroll
                     for (int j = 0; j < 9; ++j) { A[j] = row[2 * j]; Bv[j] = 0.0; }
+#if IBS_GEO_NROWS_DERIVED
+                    // The n-weighted rows (n r, n z, n l) are never loaded: with v(-n) the coefficient of -n,
+                    //   E_{n v} = k nfp (v(+n) - v(-n)) = k nfp O_v,   O_{n v} = k nfp E_v,
+                    // so the pair (E_v, O_v) just loaded feeds FOUR FMAs.  The kernel is bound by the shared-memory data pipe
+                    // (one wavefront per loaded double): 12 instead of 18 wavefronts per (m, k) here, 14 instead of 16 below.
+                    A[1] = 0.0; A[4] = 0.0; A[7] = 0.0;
+#pragma unroll
+                    for (int k = 1; k <= NT1; ++k) {
+                        const double kn = (double)k * (double)p.nfp;
+                        const double kc = kn * cn[k], ks = kn * sn[k];
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) {
+                            if (j == 1 || j == 4 || j == 7) continue;
+                            const double2 eo = *reinterpret_cast<const double2*>(row + k * ROWP_MN + 2 * j);
+                            A[j] = fma(eo.x, cn[k], A[j]);
+                            Bv[j] = fma(eo.y, sn[k], Bv[j]);
+                            if (j == 0 || j == 3 || j == 6) {
+                                A[j + 1] = fma(eo.y, kc, A[j + 1]);
+                                Bv[j + 1] = fma(eo.x, ks, Bv[j + 1]);
+                            }
+                        }
+                    }
+#else
 #pragma unroll
                     for (int k = 1; k <= NT1; ++k) {
 #pragma unroll
@@ -350,6 +376,7 @@ geometry_kernel(const GeoParams p) {
                             Bv[j] = fma(eo.y, sn[k], Bv[j]);
                         }
                     }
+#endif
                     // rows: 0 r, 1 n r, 2 r_s, 3 z, 4 n z, 5 z_s, 6 l, 7 n l, 8 l_s
                     const double dm = (double)m;
                     R += fma(cm, A[0], sm * Bv[0]);
@@ -434,6 +461,25 @@ geometry_kernel(const GeoParams p) {
                     double A[8], Bv[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { A[j] = row[2 * j]; Bv[j] = 0.0; }
+#if IBS_GEO_NROWS_DERIVED
+                    A[2] = 0.0;                           // (n b) from (b): see the (R, Z, lambda) set above
+#pragma unroll
+                    for (int k = 1; k <= NT2; ++k) {
+                        const double kn = (double)k * (double)p.nfp;
+                        const double kc = kn * cn[k], ks = kn * sn[k];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (j == 2) continue;
+                            const double2 eo = *reinterpret_cast<const double2*>(row + k * ROWP_NYQ + 2 * j);
+                            A[j] = fma(eo.x, cn[k], A[j]);
+                            Bv[j] = fma(eo.y, sn[k], Bv[j]);
+                            if (j == 1) {
+                                A[2] = fma(eo.y, kc, A[2]);
+                                Bv[2] = fma(eo.x, ks, Bv[2]);
+                            }
+                        }
+                    }
+#else
 #pragma unroll
                     for (int k = 1; k <= NT2; ++k) {
 #pragma unroll
@@ -443,6 +489,7 @@ geometry_kernel(const GeoParams p) {
                             Bv[j] = fma(eo.y, sn[k], Bv[j]);
                         }
                     }
+#endif
                     // rows: 0 g, 1 b, 2 n b, 3 b_s, 4 bsupv, 5 bsubs, 6 bsubu, 7 bsubv
                     const double dm = (double)m;
                     sqrtg += fma(cm, A[0], sm * Bv[0]);

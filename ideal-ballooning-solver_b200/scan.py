@@ -119,12 +119,24 @@ class SurfaceGather:
         self._send_full = self.recv[self.rank] if not self.dist else torch.zeros((self.nmax, 2), dtype=torch.float64, device=device)
         self.send = self._send_full[: self.nlocal]          # (nlocal, 2) contiguous view: the solver's best_out
 
-    def exchange(self) -> torch.Tensor:
-        """All-gather the send slots; returns the ``(world, nmax, 2)`` buffer (no copy, no cast)."""
+    def exchange(self, async_op: bool = False) -> torch.Tensor:
+        """All-gather the send slots; returns the ``(world, nmax, 2)`` buffer (no copy, no cast).  ``async_op=True``: the
+        collective is only enqueued (it starts when the work already queued on the current stream -- the solver that fills the
+        send slot -- is done) and the current stream does NOT wait for it: the next scan's kernels overlap it.  Call ``wait()``
+        before reading ``recv`` or refilling ``send`` (use two ``SurfaceGather`` objects alternately to keep scanning)."""
         if self.dist:
             import torch.distributed as dist
-            dist.all_gather_into_tensor(self.recv.view(-1), self._send_full.view(-1), group=self.group)
+            self.wait()
+            w = dist.all_gather_into_tensor(self.recv.view(-1), self._send_full.view(-1), group=self.group, async_op=async_op)
+            self._work = w if async_op else None
         return self.recv
+
+    def wait(self):
+        """Make the current stream wait for the pending asynchronous exchange (no-op when there is none)."""
+        w = getattr(self, "_work", None)
+        if w is not None:
+            w.wait()
+            self._work = None
 
     def unpack(self):
         """``(val (ns_total,), idx (ns_total,) int32)`` in surface order (host-side convenience, not on the timed path)."""

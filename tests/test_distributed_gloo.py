@@ -41,6 +41,21 @@ def _worker(rank, world, port, ns_total, q):
         assert buf.data_ptr() == g.recv.data_ptr()
         v2, i2 = g.unpack()
         assert torch.equal(v2, v_all) and torch.equal(i2, i_all)
+        # asynchronous form with two buffers used alternately (the bench's N > 1 path): step k's exchange is waited for in step k + 1
+        gs = [scan.SurfaceGather(ns_total, torch.device("cpu")) for _ in range(2)]
+        for k in range(5):
+            ga, gb = gs[k % 2], gs[(k + 1) % 2]
+            ga.wait()
+            ga.send[:, 0] = val + k
+            ga.send[:, 1] = idx.to(torch.float64)
+            ga.exchange(async_op=True)
+            gb.wait()
+            if k >= 1:
+                vb, ib = gb.unpack()
+                assert torch.equal(vb, v_all + (k - 1)) and torch.equal(ib, i_all)
+        gs[0].wait()
+        v4, i4 = gs[0].unpack()
+        assert torch.equal(v4, v_all + 4) and torch.equal(i4, i_all)
         q.put((rank, v_all.numpy().copy(), i_all.numpy().copy()))
     finally:
         dist.destroy_process_group()
