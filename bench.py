@@ -438,7 +438,9 @@ class Harness:
             self.sampler = ClockSampler(torch.cuda.current_device())
         # Everything that is not a step happens BEFORE the warm-up -- event creation, a generational collection of the
         # interpreter (10-100 ms when it strikes inside a step) -- so that the warm-up runs straight into the timed steps: an
-        # idle gap of a few ms between them lets the clocks drop, and the first timed step then took 4-80 ms instead of 3.6.
+        # idle gap of tens of ms between them made the first timed step take 4-80 ms instead of 3.6.  (The first step after the
+        # barrier still runs 5-30 % slow -- IBS_BENCH_DUMP_STEPS=1 prints the slowest steps and their stages; more warm-up steps,
+        # events recorded in the warm-up, synchronisations or idle gaps later in the loop do not reproduce it.)
         ev = lambda: torch.cuda.Event(enable_timing=True)
         timers = [[ev() for _ in range(nstage + 1)] for _ in range(steps)]
         import gc
