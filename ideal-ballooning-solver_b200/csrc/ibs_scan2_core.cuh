@@ -33,6 +33,9 @@ constexpr int NH = 16;            // solves per warp
 constexpr int T0 = TR + 3;        // records of stage 0: steps 0 .. 34
 constexpr int NPRE = 5;           // steps 0 .. 4 are done one at a time (start values, the end-point stencils); chunks start at step 5
 constexpr int KQ = 16;            // chain ends (and chunk ends) are multiples of KQ
+#ifndef IBS_SCAN2_EVAL4
+#define IBS_SCAN2_EVAL4 1
+#endif
 #ifndef IBS_SCAN2_EXTRAP
 #define IBS_SCAN2_EXTRAP 1
 #endif
@@ -100,7 +103,25 @@ IBS_HD EvalEnd eval_lane(Ctx& ctx, int lev, int Nl, int q_end, int q_max, double
         if (c < cmine) {                                      // (a half-warp whose chain has ended sits the chunk out)
             unsigned hist = 0;
             const unsigned enter = sign_bit(X);
-            const int nblk = (c == 0) ? (KQ - NPRE + 1) / 2 : KQ / 2;
+            const int nblk = (c == 0) ? (KQ - NPRE + 1) / 2 : KQ / 2;        // 6 or 8 pairs of steps
+#if IBS_SCAN2_EVAL4
+#pragma unroll 1
+            for (int b = 0; b < nblk / 2; ++b) {              // blocks of four steps (records two steps ahead, as before)
+                const Rec n1 = load_rec(pr);
+                chain_step(rf, th0, lam, cf, gp, X, W, S);
+                hist = (hist << 1) | sign_bit(X);
+                const Rec n2 = load_rec(pr + ds);
+                chain_step(n1, th0, lam, cf, gp, X, W, S);
+                hist = (hist << 1) | sign_bit(X);
+                const Rec n3 = load_rec(pr + 2 * ds);
+                chain_step(n2, th0, lam, cf, gp, X, W, S);
+                hist = (hist << 1) | sign_bit(X);
+                rf = load_rec(pr + 3 * ds);
+                chain_step(n3, th0, lam, cf, gp, X, W, S);
+                hist = (hist << 1) | sign_bit(X);
+                pr += 4 * ds;
+            }
+#else
 #pragma unroll 1
             for (int b = 0; b < nblk; ++b) {
                 const Rec nf = load_rec(pr);
@@ -111,6 +132,7 @@ IBS_HD EvalEnd eval_lane(Ctx& ctx, int lev, int Nl, int q_end, int q_max, double
                 hist = (hist << 1) | sign_bit(X);
                 pr += 2 * ds;
             }
+#endif
             rescale3(X, W, S);
             nodes += sign_changes_n(hist, 2 * nblk, enter);
         }
@@ -133,13 +155,15 @@ IBS_HD void eval_join(const EvalEnd& f, const EvalEnd& b, const Rec& rk, double 
 
 // ---- output passes: one sweep of one solve ---------------------------------------------------------------------------
 // general step (first rows: their stencils differ), forward arithmetic on the lane's own (possibly mirrored) row order
-template <bool WRITE>
+// CHECK (first pass only): test every row's coefficients for validity.  The prep kernel certifies whole lines (all rows, the
+// whole theta0 range); their passes run without the tests (15 of 104 instructions per two steps).
+template <bool WRITE, bool CHECK>
 IBS_HD void o_step(Sweep& sw, const Rec& rc, double th0, double lam, int qq, int row, double* Xw) {
     double g, C, F;
     coef(rc, th0, g, C, F);
     const double a = g + sw.gp;
     const double tnew = fma(-lam, F, C);
-    if (!WRITE) sw.bad |= not_pos_normal(a) | not_pos_normal(F) | not_finite(C);
+    if (!WRITE && CHECK) sw.bad |= not_pos_normal(a) | not_pos_normal(F) | not_finite(C);
     const double ia = rcp_fast(a);
     const double xn = fma(sw.w, ia, sw.x);
     sw.w = fma(-tnew, xn, sw.w);
@@ -153,8 +177,7 @@ IBS_HD void o_step(Sweep& sw, const Rec& rc, double th0, double lam, int qq, int
     const double x2 = xn * xn;
     if (par) { sw.a0o = fma(tnew, x2, sw.a0o); sw.a1o = fma(F, x2, sw.a1o); }
     else     { sw.a0e = fma(tnew, x2, sw.a0e); sw.a1e = fma(F, x2, sw.a1e); }
-    const double ax = fabs(xn);
-    if (ax > sw.vmax) { sw.vmax = ax; sw.jmax = row; }
+    if (fabs(xn) > fabs(sw.vmax)) { sw.vmax = xn; sw.jmax = row; }      // (vmax keeps the SIGNED value: no instruction for |x|)
     if (qq >= 4) {
         const double D = fma(C23, sw.W1 - sw.W3, -(C12 * (xn - sw.W4)));
         if (par) sw.aDo = fma(sw.gpp, D * D, sw.aDo); else sw.aDe = fma(sw.gpp, D * D, sw.aDe);
@@ -170,7 +193,7 @@ IBS_HD void o_step(Sweep& sw, const Rec& rc, double th0, double lam, int qq, int
 }
 
 // pipelined step: chain + sums of the current row (coefficients c) and, interleaved, the coefficients of the next row
-template <int PAR, bool WRITE>
+template <int PAR, bool WRITE, bool CHECK>
 IBS_HD void o_single(const Rec& n, double th0, double lam, OCo& c, Sweep& s, int row, double* Xw) {
     const double pA = fma(th0, n.G2, n.G1);
     const double CA = fma(th0, n.C1, n.C0);
@@ -183,7 +206,7 @@ IBS_HD void o_single(const Rec& n, double th0, double lam, OCo& c, Sweep& s, int
     double rA = 1.0 / aA;
 #endif
     const double FA = gA * n.R;
-    if (!WRITE) s.bad |= not_pos_normal(aA) | not_pos_normal(FA) | not_finite(CA);
+    if (!WRITE && CHECK) s.bad |= not_pos_normal(aA) | not_pos_normal(FA) | not_finite(CA);
     // current row
     const double xn = fma(s.w, c.ia, s.x);
     s.w = fma(-c.t, xn, s.w);
@@ -196,11 +219,10 @@ IBS_HD void o_single(const Rec& n, double th0, double lam, OCo& c, Sweep& s, int
         const double d1 = s.W1 - s.W3;
         const double x2 = xn * xn;
         const double d2 = xn - s.W4;
-        const double ax = fabs(xn);
         if (PAR) { s.a0o = fma(c.t, x2, s.a0o); s.a1o = fma(c.F, x2, s.a1o); }
         else     { s.a0e = fma(c.t, x2, s.a0e); s.a1e = fma(c.F, x2, s.a1e); }
         const double D = fma(C23, d1, -(C12 * d2));
-        if (ax > s.vmax) { s.vmax = ax; s.jmax = row; }
+        if (fabs(xn) > fabs(s.vmax)) { s.vmax = xn; s.jmax = row; }
         const double D2 = D * D;
         if (PAR) s.aDo = fma(s.gpp, D2, s.aDo); else s.aDe = fma(s.gpp, D2, s.aDe);
         s.W4 = s.W3; s.W3 = s.W2; s.W2 = s.W1; s.W1 = xn;
@@ -217,7 +239,7 @@ IBS_HD void o_single(const Rec& n, double th0, double lam, OCo& c, Sweep& s, int
 }
 
 // what the seam needs from one sweep (first pass) -- the Sweep itself is returned
-template <bool WRITE, class Ctx>
+template <bool WRITE, bool CHECK, class Ctx>
 IBS_HD Sweep out_lane(Ctx& ctx, int lev, int Nl, int q_end, int q_max, bool mirrored, double th0, double lam, double cn, int ex0, double* Xw) {
     ctx.begin_pass(lev, Nl, q_max);
     ctx.wait(0);
@@ -234,13 +256,13 @@ IBS_HD Sweep out_lane(Ctx& ctx, int lev, int Nl, int q_end, int q_max, bool mirr
         coef(load_rec(pr), th0, g, C, F);
         sw.x = 0.0; sw.w = 1.0; sw.gp = g; sw.gpp = g;
         for (int q = 1; q < NPRE; ++q)
-            o_step<WRITE>(sw, load_rec(pr + q * ds), th0, lam, q, mirrored ? Nl - 1 - q : q, Xw);
+            o_step<WRITE, CHECK>(sw, load_rec(pr + q * ds), th0, lam, q, mirrored ? Nl - 1 - q : q, Xw);
     }
     OCo cf;
     {
         bool bad = false;
         out_coef<WRITE>(load_rec(pr + NPRE * ds), th0, lam, sw.gp, cf, bad);
-        sw.bad |= bad;
+        if (CHECK) sw.bad |= bad;
     }
     Rec rf = load_rec(pr + (NPRE + 1) * ds);
     pr += (NPRE + 2) * ds;
@@ -253,14 +275,31 @@ IBS_HD Sweep out_lane(Ctx& ctx, int lev, int Nl, int q_end, int q_max, bool mirr
         const bool newstage = c >= 2 && !(c & 1);
         if (newstage) { ctx.wait(c >> 1); pr = ctx.ptr(c >> 1, KQ * c + 3); }
         if (c < cmine) {
-            const int nblk = (c == 0) ? (KQ - NPRE + 1) / 2 : KQ / 2;
+            const int nblk = (c == 0) ? (KQ - NPRE + 1) / 2 : KQ / 2;        // 6 or 8 blocks of two steps
+            if (WRITE) {
 #pragma unroll 1
-            for (int b = 0; b < nblk; ++b) {                  // steps q (odd), q + 1 (even)
-                const Rec nf = load_rec(pr);
-                o_single<1, WRITE>(rf, th0, lam, cf, sw, row, Xw);
-                rf = load_rec(pr + ds);
-                o_single<0, WRITE>(nf, th0, lam, cf, sw, row + dr, Xw);
-                pr += 2 * ds; row += 2 * dr;
+                for (int b = 0; b < nblk; ++b) {              // steps q (odd), q + 1 (even)
+                    const Rec nf = load_rec(pr);
+                    o_single<1, WRITE, CHECK>(rf, th0, lam, cf, sw, row, Xw);
+                    rf = load_rec(pr + ds);
+                    o_single<0, WRITE, CHECK>(nf, th0, lam, cf, sw, row + dr, Xw);
+                    pr += 2 * ds; row += 2 * dr;
+                }
+            } else {
+                // first pass: blocks of FOUR steps -- the five-row window W1..W4 of the derivative stencil rotates once per
+                // block, so no register moves are left (21 of 104 instructions per two steps in the two-step form)
+#pragma unroll 1
+                for (int b = 0; b < nblk / 2; ++b) {
+                    const Rec n1 = load_rec(pr);
+                    o_single<1, WRITE, CHECK>(rf, th0, lam, cf, sw, row, Xw);
+                    const Rec n2 = load_rec(pr + ds);
+                    o_single<0, WRITE, CHECK>(n1, th0, lam, cf, sw, row + dr, Xw);
+                    const Rec n3 = load_rec(pr + 2 * ds);
+                    o_single<1, WRITE, CHECK>(n2, th0, lam, cf, sw, row + 2 * dr, Xw);
+                    rf = load_rec(pr + 3 * ds);
+                    o_single<0, WRITE, CHECK>(n3, th0, lam, cf, sw, row + 3 * dr, Xw);
+                    pr += 4 * ds; row += 4 * dr;
+                }
             }
             q += 2 * nblk;
             sweep_rescale<WRITE>(sw);
@@ -299,14 +338,14 @@ IBS_HD void out_join(const Sweep& f, const Sweep& b, const Rec& rk, double th0, 
         const double S = fma(zf2, f.a1o + f.a1e, zb2 * (b.a1o + b.a1e)) - Fk;
         o.dlt = r / S;
     }
-    const double mf = f.vmax * fabs(zf), mb = b.vmax * fabs(zb);
+    const double mf = fabs(f.vmax) * fabs(zf), mb = fabs(b.vmax) * fabs(zb);
     o.zmax = fmax(mf, mb);
     o.jmax = (mb > mf) ? b.jmax : f.jmax;
     if (!(o.zmax == o.zmax)) o.zmax = 1e308;
 }
 
 // ---- the state machine of one solve (both lanes of a pair run it identically) -----------------------------------------
-// Ctx supplies:  eval(lev, Nl, k, th0, lam, r, S, nodes);  out1(lev, Nl, k, th0, lam, SolveOut&);  out2(lev, Nl, k, th0, lam,
+// Ctx supplies:  eval(lev, Nl, k, th0, lam, r, S, nodes);  out1(lev, Nl, k, th0, lam, SolveOut&, check);  out2(lev, Nl, k, th0, lam,
 // SolveOut, Xw);  all / any / min_i / max_i / first_i;  fixup(wr, X, dX, N, bad, h, want_dX);
 // warm_in(token, lev) / warm_out(token, lev, value): the per-level eigenvalues of the theta0 NEIGHBOUR (one grid step away,
 // solved earlier: token w_in, -1 = none) and of this solve for its own neighbour (token w_out, -1 = nobody needs them).
@@ -350,7 +389,7 @@ IBS_HD void solve_item2(Ctx& ctx, const ItemProblem& P, double th0, bool act, do
     for (;;) {
         const int kind = (phase == PH_ITER || phase == PH_SIGMA) ? 1 : (phase == PH_PEAK || phase == PH_O1) ? 2 : 3;
         if (kind == 1) ctx.eval(lev, Nl, k, th0, sh, r, S, nodes);
-        else if (kind == 2) ctx.out1(lev, Nl, k, th0, sh, out);
+        else if (kind == 2) ctx.out1(lev, Nl, k, th0, sh, out, !P.safe);
         else ctx.out2(lev, Nl, k, th0, sh, out, (wr && !out.bad) ? Xrow : nullptr);
         if (phase == PH_ITER || phase == PH_SIGMA) {
             if (phase == PH_SIGMA) {

@@ -896,6 +896,7 @@ struct ItemProblem {
     int N, nlev;
     double h, U, Lb;
     bool want_X, want_dX;
+    bool safe = false;      // lane-per-chain kernel: the prep kernel has certified every row of the line for the whole theta0 range
 };
 struct ItemResult { double gam, rho; int info; };
 

@@ -39,6 +39,7 @@ constexpr int SC_WARPS = IBS_SCAN_WARPS;           // warps per CTA (they never 
 struct ScanParams {
     const double* poly;       // [nline][rows_total][REC]
     const double* bounds;     // [nline][2]: U, Lb
+    const int* line_safe;     // [nline]: 1 = every row of the line has valid coefficients on the whole theta0 range (scan_prep_kernel)
     const double* theta0;     // [nline * nth0]
     const double* sigma;      // nullable
     int nline, nth0, N, nlev, rows_total, groups, nitems;
@@ -361,10 +362,12 @@ struct Dev2Ctx {
         ot.X = xd(me.X); ot.W = xd(me.W); ot.S = xd(me.S); ot.nodes = xi(me.nodes);
         scan2::eval_join(h ? ot : me, h ? me : ot, rec_k(k), th0, lam, r, S, nodes);
     }
-    __device__ __forceinline__ void out1(int lev, int Nl_, int k, double th0, double lam, SolveOut& out) {
+    __device__ __forceinline__ void out1(int lev, int Nl_, int k, double th0, double lam, SolveOut& out, bool check) {
         const int qf = k, qb = Nl_ - 1 - k;
         prefetch_k(lev, k);
-        const Sweep me = scan2::out_lane<false>(*this, lev, Nl_, h ? qb : qf, qf > qb ? qf : qb, h != 0, th0, lam, 0.0, 0, nullptr);
+        // (check is warp-uniform: a property of the line)
+        const Sweep me = check ? scan2::out_lane<false, true>(*this, lev, Nl_, h ? qb : qf, qf > qb ? qf : qb, h != 0, th0, lam, 0.0, 0, nullptr)
+                               : scan2::out_lane<false, false>(*this, lev, Nl_, h ? qb : qf, qf > qb ? qf : qb, h != 0, th0, lam, 0.0, 0, nullptr);
         Sweep ot;
         ot.x = xd(me.x); ot.w = xd(me.w); ot.E = xi(me.E); ot.W2 = xd(me.W2); ot.W3 = xd(me.W3); ot.W4 = xd(me.W4); ot.gp = xd(me.gp); ot.gpp = xd(me.gpp);
         ot.a0e = xd(me.a0e); ot.a0o = xd(me.a0o); ot.a1e = xd(me.a1e); ot.a1o = xd(me.a1o); ot.aDe = xd(me.aDe); ot.aDo = xd(me.aDo);
@@ -375,7 +378,7 @@ struct Dev2Ctx {
         const int qf = k, qb = Nl_ - 1 - k;
         const bool ok = !out.bad && out.zmax > 0.0 && out.zmax < 1e300;
         const double xk = h ? out.xkb : out.xkf;
-        scan2::out_lane<true>(*this, lev, Nl_, h ? qb : qf, qf > qb ? qf : qb, h != 0, th0, lam, ok ? NORM_INFLATE / (xk * out.zmax) : 0.0,
+        scan2::out_lane<true, false>(*this, lev, Nl_, h ? qb : qf, qf > qb ? qf : qb, h != 0, th0, lam, ok ? NORM_INFLATE / (xk * out.zmax) : 0.0,
                               -(h ? out.Ekb : out.Ekf), Xw);
     }
     __device__ __forceinline__ bool all(bool b) const { return __all_sync(FULL, b); }
@@ -447,6 +450,7 @@ scan2_solve_kernel(const ScanParams p) {
         ItemProblem P;
         P.N = N; P.nlev = p.nlev; P.h = p.h; P.U = p.bounds[2 * line]; P.Lb = p.bounds[2 * line + 1];
         P.want_X = p.X_rows != nullptr; P.want_dX = p.dX_out != nullptr;
+        P.safe = p.line_safe[line] != 0;
         ctx.line_base = p.poly + (size_t)line * p.rows_total * REC;
         int w_in = -1, w_out = -1;
         if (p.warm) {
@@ -540,7 +544,8 @@ struct PMin { __device__ __forceinline__ double operator()(double a, double b) c
 
 __global__ void __launch_bounds__(PREP_T)
 scan_prep_kernel(const double* __restrict__ base, const double* __restrict__ dPdrho, const double* __restrict__ theta0, int nth0,
-                 int N, double h2, int nlev, int rows_total, double* __restrict__ poly, double* __restrict__ bounds) {
+                 int N, double h2, int nlev, int rows_total, double* __restrict__ poly, double* __restrict__ bounds,
+                 int* __restrict__ line_safe) {
     __shared__ double scratch[PREP_T / 32];
     const int line = blockIdx.x, tid = threadIdx.x;
     const double* b = base + (size_t)line * IBS_NBASE * N;
@@ -564,6 +569,7 @@ scan_prep_kernel(const double* __restrict__ base, const double* __restrict__ dPd
     gmax = block_reduce(gmax, PMax(), scratch);
     const double sg = (gmax > 0.0 && gmax < 1e300) ? pow2(-exp_max2(gmax, 0.0)) : 1.0;
     double U = -1e300, minC = 1e300, maxg = 0.0, minF = 1e300, maxF = 0.0;
+    double unsafe = 0.0;                                  // 1: some row could hold an invalid coefficient for some theta0 of the range
     double* out = poly + (size_t)line * rows_total * REC;
     for (int j = tid; j < N; j += PREP_T) {
         Rec r = record(j);
@@ -571,6 +577,13 @@ scan_prep_kernel(const double* __restrict__ base, const double* __restrict__ dPd
         double gmn, gmx, cmn, cmx;
         record_ranges(r, t0, t1, gmn, gmx, cmn, cmx);
         maxg = fmax(maxg, gmx);
+        {
+            // what the first output pass would test row by row (a = g + g' and F = g R positive and normal, C finite), certified
+            // here for the whole theta0 range and all levels (R and C carry up to 4^MAXLEV there); NaN fails every comparison
+            const double Fmn = gmn * r.R, Fmx = gmx * r.R;
+            const bool ok = gmn >= 1e-290 && gmx <= 1e290 && Fmn >= 1e-290 && Fmx <= 1e290 && cmn >= -1e290 && cmx <= 1e290;
+            if (!ok) unsafe = 1.0;
+        }
         if (j >= 1 && j <= N - 2) {
             const double Fmin = gmn * r.R, Fmax = gmx * r.R;
             U = fmax(U, cmx >= 0.0 ? cmx / Fmin : cmx / Fmax);
@@ -592,7 +605,9 @@ scan_prep_kernel(const double* __restrict__ base, const double* __restrict__ dPd
     maxg = block_reduce(maxg, PMax(), scratch);
     minF = block_reduce(minF, PMin(), scratch);
     maxF = block_reduce(maxF, PMax(), scratch);
+    unsafe = block_reduce(unsafe, PMax(), scratch);
     if (tid == 0) {
+        line_safe[line] = unsafe == 0.0 ? 1 : 0;
         U = U + 1e-12 * fabs(U) + 1e-300;
         const double numer = minC - 8.0 * maxg;
         bounds[2 * line + 0] = U;
@@ -678,6 +693,7 @@ static int scan_solve_lines(const SolveParams& p, int l0, int nline, int spl, bo
     auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_poly = take((size_t)nline * rows_total * REC * sizeof(double));
     const size_t o_bounds = take((size_t)nline * 2 * sizeof(double));
+    const size_t o_safe = take((size_t)nline * sizeof(int));
     // lane-per-chain kernel: column order of the lines + warm start from the previous line (see scan2_solve_kernel); a round
     // is at least IBS_SCAN_WARM_SPACING (default 2) x the resident warps, so that a line's predecessor has normally finished
     int lc = nline, rounds = 1;
@@ -709,7 +725,7 @@ static int scan_solve_lines(const SolveParams& p, int l0, int nline, int spl, bo
     IBS_CUDA_CHECK(cudaMallocAsync((void**)&ws, off + 256, stream));
     int rc = IBS_OK;
     ScanParams sp;
-    sp.poly = (double*)(ws + o_poly); sp.bounds = (double*)(ws + o_bounds); sp.counter = (unsigned*)(ws + o_zero);
+    sp.poly = (double*)(ws + o_poly); sp.bounds = (double*)(ws + o_bounds); sp.line_safe = (int*)(ws + o_safe); sp.counter = (unsigned*)(ws + o_zero);
     sp.theta0 = p.theta0 + v0; sp.sigma = p.sigma ? p.sigma + v0 : nullptr;
     sp.nline = nline; sp.nth0 = p.nth0; sp.N = N; sp.nlev = nlev; sp.rows_total = rows_total;
     sp.groups = groups;
@@ -737,7 +753,7 @@ static int scan_solve_lines(const SolveParams& p, int l0, int nline, int spl, bo
         rc = cuda_fail(e, "cudaMemsetAsync(scan counters)");
     if (rc == IBS_OK) {
         scan_prep_kernel<<<nline, PREP_T, 0, stream>>>(p.base + (size_t)l0 * IBS_NBASE * N, p.dPdrho + l0, sp.theta0, p.nth0, N, p.h * p.h, nlev,
-                                                       rows_total, (double*)(ws + o_poly), (double*)(ws + o_bounds));
+                                                       rows_total, (double*)(ws + o_poly), (double*)(ws + o_bounds), (int*)(ws + o_safe));
         if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) rc = cuda_fail(e, "scan_prep_kernel launch");
     }
     if (rc == IBS_OK && s2) {

@@ -35,10 +35,16 @@ struct Host2Ctx {
         if (getenv("IBS_HOST_TRACE")) printf("  lev %d Nl %d k %d lam %.15g rho %.15g r %.3e S %.3e nodes %d\n", lev, Nl_, k, lam, lam + r / S, r, S, nodes);
         passes += 1; cost += (double)Nl_ / N;
     }
-    void out1(int lev, int Nl_, int k, double th0, double lam, SolveOut& out) {
+    void out1(int lev, int Nl_, int k, double th0, double lam, SolveOut& out, bool check = true) {
         const int qf = k, qb = Nl_ - 1 - k, qm = qf > qb ? qf : qb;
-        h = 0; const Sweep f = out_lane<false>(*this, lev, Nl_, qf, qm, false, th0, lam, 0.0, 0, nullptr);
-        h = 1; const Sweep b = out_lane<false>(*this, lev, Nl_, qb, qm, true, th0, lam, 0.0, 0, nullptr);
+        Sweep f, b;
+        if (check) {
+            h = 0; f = out_lane<false, true>(*this, lev, Nl_, qf, qm, false, th0, lam, 0.0, 0, nullptr);
+            h = 1; b = out_lane<false, true>(*this, lev, Nl_, qb, qm, true, th0, lam, 0.0, 0, nullptr);
+        } else {
+            h = 0; f = out_lane<false, false>(*this, lev, Nl_, qf, qm, false, th0, lam, 0.0, 0, nullptr);
+            h = 1; b = out_lane<false, false>(*this, lev, Nl_, qb, qm, true, th0, lam, 0.0, 0, nullptr);
+        }
         out_join(f, b, rec_k(k), th0, lam, k, out);
         if (lev == 0) nev_lev[7] += 1;                       // first output passes on the fine level (slot 7 of the counts)
         if (getenv("IBS_HOST_TRACE")) printf("  O1 lev %d k %d lam %.15g dlt %.3e gam %.15g zmax %.3e\n", lev, k, lam, out.dlt, out.gam, out.zmax);
@@ -47,8 +53,8 @@ struct Host2Ctx {
     void out2(int lev, int Nl_, int k, double th0, double lam, const SolveOut& out, double* Xw) {
         const int qf = k, qb = Nl_ - 1 - k, qm = qf > qb ? qf : qb;
         const bool ok = !out.bad && out.zmax > 0.0 && out.zmax < 1e300;
-        h = 0; out_lane<true>(*this, lev, Nl_, qf, qm, false, th0, lam, ok ? NORM_INFLATE / (out.xkf * out.zmax) : 0.0, -out.Ekf, Xw);
-        h = 1; out_lane<true>(*this, lev, Nl_, qb, qm, true, th0, lam, ok ? NORM_INFLATE / (out.xkb * out.zmax) : 0.0, -out.Ekb, Xw);
+        h = 0; out_lane<true, false>(*this, lev, Nl_, qf, qm, false, th0, lam, ok ? NORM_INFLATE / (out.xkf * out.zmax) : 0.0, -out.Ekf, Xw);
+        h = 1; out_lane<true, false>(*this, lev, Nl_, qb, qm, true, th0, lam, ok ? NORM_INFLATE / (out.xkb * out.zmax) : 0.0, -out.Ekb, Xw);
         passes += 1; cost += (double)Nl_ / N;
     }
     bool all(bool b) const { return b; }
