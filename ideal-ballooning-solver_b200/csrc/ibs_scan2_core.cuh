@@ -33,8 +33,11 @@ constexpr int NH = 16;            // solves per warp
 constexpr int T0 = TR + 3;        // records of stage 0: steps 0 .. 34
 constexpr int NPRE = 5;           // steps 0 .. 4 are done one at a time (start values, the end-point stencils); chunks start at step 5
 constexpr int KQ = 16;            // chain ends (and chunk ends) are multiples of KQ
+#ifndef IBS_SCAN2_RCP_EXTRA
+#define IBS_SCAN2_RCP_EXTRA 0       // one more Newton step on the reciprocal of the output passes: not needed (see o_single); 2.93 -> 2.84 ms without
+#endif
 #ifndef IBS_SCAN2_EVAL4
-#define IBS_SCAN2_EVAL4 1
+#define IBS_SCAN2_EVAL4 0          // iteration pass in blocks of four steps: measured 2.97 vs 2.92 ms (two-step blocks stay)
 #endif
 #ifndef IBS_SCAN2_EXTRAP
 #define IBS_SCAN2_EXTRAP 1
@@ -230,8 +233,8 @@ IBS_HD void o_single(const Rec& n, double th0, double lam, OCo& c, Sweep& s, int
     }
     s.gp = c.g;
     eA = fma(eA, eA, eA);
-    rA = fma(rA, eA, rA);
-#if defined(__CUDA_ARCH__)
+    rA = fma(rA, eA, rA);                                 // seed 2^-23 -> (2^-23)^3: below the rounding of a double
+#if defined(__CUDA_ARCH__) && IBS_SCAN2_RCP_EXTRA
     eA = fma(-aA, rA, 1.0);
     rA = fma(rA, eA, rA);
 #endif
