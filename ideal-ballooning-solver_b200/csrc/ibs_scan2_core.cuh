@@ -146,10 +146,13 @@ IBS_HD EvalEnd eval_lane(Ctx& ctx, int lev, int Nl, int q_end, int q_max, double
 }
 
 // join of the two chains at row k: twisted residual r' and S' = sum 2F z^2 (z_k = 1), node count
-IBS_HD void eval_join(const EvalEnd& f, const EvalEnd& b, const Rec& rk, double th0, double lam, double& r, double& S, int& nodes) {
-    double g, C, F;
-    coef(rk, th0, g, C, F);
-    const double tk = fma(-lam, F, C);
+// (t_k, F_k) of the matching row from its record
+IBS_HD void row_tF(const Rec& rk, double th0, double lam, double& tk, double& Fk) {
+    double g, C;
+    coef(rk, th0, g, C, Fk);
+    tk = fma(-lam, Fk, C);
+}
+IBS_HD void eval_join(const EvalEnd& f, const EvalEnd& b, double tk, double F, double th0, double lam, double& r, double& S, int& nodes) {
     const double ixf = 1.0 / f.X, ixb = 1.0 / b.X;
     r = -(f.W * ixf + b.W * ixb + tk);
     S = fma(f.S * ixf, ixf, b.S * ixb * ixb) - F;            // row k was counted by both chains
@@ -316,10 +319,7 @@ IBS_HD Sweep out_lane(Ctx& ctx, int lev, int Nl, int q_end, int q_max, bool mirr
 // seam (rows k-1, k, k+1) and totals of the first output pass: Simpson Rayleigh quotient, max |z| and its row, validity,
 // and the two sweeps' value / scale at row k for the writing pass.  f: forward sweep, b: backward (mirrored) sweep; both
 // have counted row k in their X^2 sums (taken out here with t_k, F_k of the record rk).
-IBS_HD void out_join(const Sweep& f, const Sweep& b, const Rec& rk, double th0, double lam, int k, SolveOut& o) {
-    double gk, Ck, Fk;
-    coef(rk, th0, gk, Ck, Fk);
-    const double tk = fma(-lam, Fk, Ck);
+IBS_HD void out_join(const Sweep& f, const Sweep& b, double tk, double Fk, double th0, double lam, int k, SolveOut& o) {
     o.xkf = f.x; o.xkb = b.x; o.Ekf = f.E; o.Ekb = b.E;
     o.bad = f.bad | b.bad;
     const double zf = 1.0 / f.x, zb = 1.0 / b.x;

@@ -273,6 +273,9 @@ scan_solve_kernel(const ScanParams p) {
 #ifndef IBS_SCAN2_CTAS
 #define IBS_SCAN2_CTAS 4          // CTAs of 4 warps per SM the kernel is compiled for (register cap 65536 / (128 * CTAS))
 #endif
+#ifndef IBS_SCAN2_ROWK_SMEM
+#define IBS_SCAN2_ROWK_SMEM 0       // matching row from the ring instead of L2: measured 2.89 vs 2.81 ms (select + shuffles cost more than the hidden L2 read)
+#endif
 #ifndef IBS_SCAN2_PREFETCH_K
 #define IBS_SCAN2_PREFETCH_K 0      // measured: 3.09 vs 3.03 ms with the prefetch (the L1 line rarely survives until the join)
 #endif
@@ -347,6 +350,22 @@ struct Dev2Ctx {
         asm volatile("prefetch.global.L1 [%0];" :: "l"(q + REC - 1));       // (a 48-byte record may straddle two 32-byte sectors' lines)
 #endif
     }
+    // (t_k, F_k) of the matching row for the join of a pass.  Row k is the LAST row both chains process, so its record is still
+    // in the ring -- for the lane whose chain is the longer one (the ring runs on for it; the shorter chain's last stage may
+    // have been overwritten): that lane reads it from shared memory and hands the two numbers to its partner.  (It used to
+    // be an L2 round trip per pass, ~9 per item, exposed at the join.)
+    __device__ __forceinline__ void row_k(int Nl_, int k, double th0, double lam, double& tk, double& Fk) const {
+#if IBS_SCAN2_ROWK_SMEM
+        const int qf = k, qb = Nl_ - 1 - k, qe = h ? qb : qf;
+        const bool mine = h ? (qb > qf) : (qf >= qb);                         // my chain is the longer one (ties: the forward lane)
+        double t = 0.0, F = 0.0;
+        if (mine) scan2::row_tF(load_rec(ptr(scan2::stage_of(qe), qe)), th0, lam, t, F);
+        const double to = xd(t), Fo = xd(F);
+        tk = mine ? t : to; Fk = mine ? F : Fo;
+#else
+        scan2::row_tF(rec_k(k), th0, lam, tk, Fk);
+#endif
+    }
     __device__ __forceinline__ Rec rec_k(int k) const {        // record of the matching row (global memory; L2)
         const double2* q = reinterpret_cast<const double2*>(lvl + (size_t)k * REC);
         const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
@@ -360,7 +379,9 @@ struct Dev2Ctx {
         const scan2::EvalEnd me = scan2::eval_lane(*this, lev, Nl_, h ? qb : qf, qf > qb ? qf : qb, th0, lam);
         scan2::EvalEnd ot;
         ot.X = xd(me.X); ot.W = xd(me.W); ot.S = xd(me.S); ot.nodes = xi(me.nodes);
-        scan2::eval_join(h ? ot : me, h ? me : ot, rec_k(k), th0, lam, r, S, nodes);
+        double tk, Fk;
+        row_k(Nl_, k, th0, lam, tk, Fk);
+        scan2::eval_join(h ? ot : me, h ? me : ot, tk, Fk, th0, lam, r, S, nodes);
     }
     __device__ __forceinline__ void out1(int lev, int Nl_, int k, double th0, double lam, SolveOut& out, bool check) {
         const int qf = k, qb = Nl_ - 1 - k;
@@ -372,7 +393,9 @@ struct Dev2Ctx {
         ot.x = xd(me.x); ot.w = xd(me.w); ot.E = xi(me.E); ot.W2 = xd(me.W2); ot.W3 = xd(me.W3); ot.W4 = xd(me.W4); ot.gp = xd(me.gp); ot.gpp = xd(me.gpp);
         ot.a0e = xd(me.a0e); ot.a0o = xd(me.a0o); ot.a1e = xd(me.a1e); ot.a1o = xd(me.a1o); ot.aDe = xd(me.aDe); ot.aDo = xd(me.aDo);
         ot.aEnd = xd(me.aEnd); ot.vmax = xd(me.vmax); ot.jmax = xi(me.jmax); ot.bad = xi((int)me.bad) != 0;
-        scan2::out_join(h ? ot : me, h ? me : ot, rec_k(k), th0, lam, k, out);
+        double tk, Fk;
+        row_k(Nl_, k, th0, lam, tk, Fk);
+        scan2::out_join(h ? ot : me, h ? me : ot, tk, Fk, th0, lam, k, out);
     }
     __device__ __forceinline__ void out2(int lev, int Nl_, int k, double th0, double lam, const SolveOut& out, double* Xw) {
         const int qf = k, qb = Nl_ - 1 - k;

@@ -30,7 +30,9 @@ struct Host2Ctx {
         const int qf = k, qb = Nl_ - 1 - k, qm = qf > qb ? qf : qb;
         h = 0; const EvalEnd f = eval_lane(*this, lev, Nl_, qf, qm, th0, lam);
         h = 1; const EvalEnd b = eval_lane(*this, lev, Nl_, qb, qm, th0, lam);
-        eval_join(f, b, rec_k(k), th0, lam, r, S, nodes);
+        double tk, Fk;
+        row_tF(rec_k(k), th0, lam, tk, Fk);
+        eval_join(f, b, tk, Fk, th0, lam, r, S, nodes);
         nev_lev[lev & 7] += 1;
         if (getenv("IBS_HOST_TRACE")) printf("  lev %d Nl %d k %d lam %.15g rho %.15g r %.3e S %.3e nodes %d\n", lev, Nl_, k, lam, lam + r / S, r, S, nodes);
         passes += 1; cost += (double)Nl_ / N;
@@ -45,7 +47,9 @@ struct Host2Ctx {
             h = 0; f = out_lane<false, false>(*this, lev, Nl_, qf, qm, false, th0, lam, 0.0, 0, nullptr);
             h = 1; b = out_lane<false, false>(*this, lev, Nl_, qb, qm, true, th0, lam, 0.0, 0, nullptr);
         }
-        out_join(f, b, rec_k(k), th0, lam, k, out);
+        double tk, Fk;
+        row_tF(rec_k(k), th0, lam, tk, Fk);
+        out_join(f, b, tk, Fk, th0, lam, k, out);
         if (lev == 0) nev_lev[7] += 1;                       // first output passes on the fine level (slot 7 of the counts)
         if (getenv("IBS_HOST_TRACE")) printf("  O1 lev %d k %d lam %.15g dlt %.3e gam %.15g zmax %.3e\n", lev, k, lam, out.dlt, out.gam, out.zmax);
         passes += 1; cost += (double)Nl_ / N;
