@@ -33,6 +33,12 @@ constexpr int GEO_THREADS = 128;          // axisymmetric tables: 128-point tile
 #ifndef IBS_GEO_THREADS_3D
 #define IBS_GEO_THREADS_3D 128
 #endif
+#ifndef IBS_GEO_KC_INLOOP
+#define IBS_GEO_KC_INLOOP 0
+#endif
+#ifndef IBS_GEO_MINB
+#define IBS_GEO_MINB 1
+#endif
 #ifndef IBS_GEO_NROWS_DERIVED
 #define IBS_GEO_NROWS_DERIVED 1
 #endif
@@ -183,7 +189,7 @@ __device__ __forceinline__ void geo_point_epilogue(const GeoParams& p, const Geo
 }
 
 template <int NT1, int NT2>
-__global__ void __launch_bounds__(GeoThreads<NT1>::value)
+__global__ void __launch_bounds__(GeoThreads<NT1>::value, (NT1 > 0) ? IBS_GEO_MINB : 1)
 geometry_kernel(const GeoParams p) {
     constexpr int W1 = 2 * NT1 + 1, W2 = 2 * NT2 + 1, NT = (NT1 > NT2 ? NT1 : NT2);
     constexpr int GEO_THREADS = GeoThreads<NT1>::value;
@@ -353,7 +359,10 @@ geometry_kernel(const GeoParams p) {
 #pragma unroll
                     for (int k = 1; k <= NT1; ++k) {
                         const double kn = (double)k * (double)p.nfp;
-                        const double kc = kn * cn[k], ks = kn * sn[k];
+                        double kc = kn * cn[k], ks = kn * sn[k];
+#if IBS_GEO_KC_INLOOP
+                        asm volatile("" : "+d"(kc), "+d"(ks));       // (formed here, per m: hoisted they cost 4 NT1 registers)
+#endif
 #pragma unroll
                         for (int j = 0; j < 9; ++j) {
                             if (j == 1 || j == 4 || j == 7) continue;
@@ -466,7 +475,10 @@ geometry_kernel(const GeoParams p) {
 #pragma unroll
                     for (int k = 1; k <= NT2; ++k) {
                         const double kn = (double)k * (double)p.nfp;
-                        const double kc = kn * cn[k], ks = kn * sn[k];
+                        double kc = kn * cn[k], ks = kn * sn[k];
+#if IBS_GEO_KC_INLOOP
+                        asm volatile("" : "+d"(kc), "+d"(ks));
+#endif
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             if (j == 2) continue;

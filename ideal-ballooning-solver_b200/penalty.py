@@ -4,8 +4,11 @@ its forward-difference Jacobian, exactly as the reference's optimiser forms them
 ``sims_runner_NCSX.py:313``:  ``f0 = f0 + prefac[-1] * sum(max(gamma_ball - gamma_ball_thresh, 0))``, returned as ``sqrt(f0)``;
 ``sims_runner_NCSX.py:254-261``: ``df0[i] = (f0_i - f0_0) / step_i * 0.5 / sqrt(f0_0)``.
 Second half of f3: ``hf_jacobian`` forms the same Jacobian from ONE scan of the base equilibrium plus the first-order
-change of every surface's maximum growth rate under each perturbed equilibrium (``scan.hellmann_feynman_gamma``: K1 on
-the arg-max field lines + one K4 contraction per degree of freedom, no eigen-solve) instead of ``ndofs + 1`` full scans.
+change of every surface's maximum growth rate under each perturbed equilibrium instead of ``ndofs + 1`` full scans.  That
+change comes either from ``scan.table_gradient(...).predict(tables0, tables_pert)`` -- reverse mode through K1
+(``ibs_geometry_adjoint``): the gradient with respect to every Fourier table coefficient once, then one dot product per
+degree of freedom -- or from ``scan.hellmann_feynman_gamma`` (K1 on the arg-max field lines of each perturbed table set +
+one K4 contraction, no eigen-solve), its finite-perturbation form.
 The perturbed equilibria themselves (VMEC runs) stay outside this package.
 """
 from __future__ import annotations
@@ -44,7 +47,7 @@ def fd_jacobian(f0_other, gamma_ball_all, step_arr, thresh: float = GAMMA_BALL_T
 
 def hf_jacobian(f0_other, gamma_base, dgamma, step_arr, thresh: float = GAMMA_BALL_THRESH["NCSX"], prefac: float = PREFAC_BALL):
     """As ``fd_jacobian``, with the growth rates of the perturbed equilibria predicted to first order:
-    ``gamma_i = gamma_base + dgamma[i - 1]`` (``scan.hellmann_feynman_gamma``).  ``f0_other`` has ``ndofs + 1`` entries
+    ``gamma_i = gamma_base + dgamma[i - 1]`` (``scan.TableGradient.predict`` or ``scan.hellmann_feynman_gamma``).  ``f0_other`` has ``ndofs + 1`` entries
     (0 = base), ``dgamma`` is ``(ndofs, ns)``."""
     gamma_base = np.asarray(gamma_base, dtype=np.float64)
     dgamma = np.asarray(dgamma, dtype=np.float64).reshape(-1, gamma_base.size)
