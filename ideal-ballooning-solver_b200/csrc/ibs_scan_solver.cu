@@ -497,31 +497,37 @@ scan2_solve_kernel(const ScanParams p) {
         }
         ItemResult res;
         scan2::solve_item2(ctx, P, th0, act, sg, p.sigma != nullptr, Xrow, dXrow, res, cold, w_in, w_out);
-        if (w_out >= 0) {
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) *reinterpret_cast<volatile unsigned*>(p.warm_flag + slot) = 1u;
-        }
         if (act && h == 0) {
             p.lam_out[sidx] = res.gam;
             if (p.lam_matrix_out) p.lam_matrix_out[sidx] = res.rho;
             if (p.info_out) p.info_out[sidx] = res.info;
         }
-        if (p.items_per_surface > 0) {
-            // ---- fused arg-max (see scan_solve_kernel): the forward lanes carry the solves
-            const int surf = line / p.lines_per_surface;
-            double bv = -INFINITY; int bi = 0x7fffffff, anynan = 0;
+        // ---- publication of this item: its warm-start record (written inside solve_item2) and, for the fused arg-max (see
+        // scan_solve_kernel; the forward lanes carry the solves), its best (value, index) -- ONE fence for both (a fence
+        // waits for the warp's outstanding stores, here the whole X output of the writing pass: ~2 % of the kernel each)
+        const bool fused = p.items_per_surface > 0;
+        const int surf = line / p.lines_per_surface;
+        double bv = -INFINITY; int bi = 0x7fffffff, anynan = 0;
+        if (fused) {
             if (act && h == 0) {
                 const double v = res.gam;
                 if (v != v) anynan = 1;
                 best_merge(bv, bi, v, (line - surf * p.lines_per_surface) * p.nth0 + idx);
             }
             warp_best(bv, bi, anynan);
-            unsigned prev = 0;
             if (lane == 0) {
                 p.item_val[slot] = bv;
                 p.item_idx[slot] = anynan ? -2 : bi;
-                __threadfence();
+            }
+        }
+        if (fused || w_out >= 0) {
+            __threadfence();
+            __syncwarp();
+        }
+        if (fused) {
+            unsigned prev = 0;
+            if (lane == 0) {
+                if (w_out >= 0) *reinterpret_cast<volatile unsigned*>(p.warm_flag + slot) = 1u;
                 prev = atomicAdd(&p.surf_count[surf], 1u);
             }
             prev = __shfl_sync(FULL, prev, 0);
@@ -544,6 +550,8 @@ scan2_solve_kernel(const ScanParams p) {
                     if (p.sigma0_out) p.sigma0_out[surf] = sgm;
                 }
             }
+        } else if (w_out >= 0 && lane == 0) {
+            *reinterpret_cast<volatile unsigned*>(p.warm_flag + slot) = 1u;
         }
     }
 }
