@@ -457,7 +457,8 @@ class Harness:
                 self.flush.zero_()
                 if _ % 8 == 7:
                     torch.cuda.synchronize()
-                    if time.perf_counter() - t_ramp > float(os.environ.get("IBS_BENCH_RAMP_S", "0.3")):
+                    # (every rank must run the same number of steps -- a step may hold a collective: the ranks agree on "time is up")
+                    if self.max_over_ranks(time.perf_counter() - t_ramp) > float(os.environ.get("IBS_BENCH_RAMP_S", "0.3")):
                         break
             for _ in range(warmup):
                 step(None)
