@@ -350,10 +350,11 @@ IBS_HD void out_join(const Sweep& f, const Sweep& b, double tk, double Fk, doubl
 // ---- the state machine of one solve (both lanes of a pair run it identically) -----------------------------------------
 // Ctx supplies:  eval(lev, Nl, k, th0, lam, r, S, nodes);  out1(lev, Nl, k, th0, lam, SolveOut&, check);  out2(lev, Nl, k, th0, lam,
 // SolveOut, Xw);  all / any / min_i / max_i / first_i;  fixup(wr, X, dX, N, bad, h, want_dX);
-// warm_in(token, lev) / warm_out(token, lev, value): the per-level eigenvalues of the theta0 NEIGHBOUR (one grid step away,
-// solved earlier: token w_in, -1 = none) and of this solve for its own neighbour (token w_out, -1 = nobody needs them).
+// warm_in(token, lev) / warm_out(token, lev, value): the per-level eigenvalues of the NEIGHBOUR -- the same theta0 on the previous
+// field line of the batch (the adjacent surface / alpha of a scan grid), solved one round earlier: token w_in, -1 = none -- and
+// of this solve for its own successor (token w_out, -1 = nobody needs them).
 //
-// Warm start.  lam_max is smooth in theta0, and so is the error of every start value below: with the neighbour's level
+// Warm start.  lam_max is smooth along the scan grid, and so is the error of every start value below: with the neighbour's level
 // eigenvalues n_l known, the coarsest level starts at n_nlev instead of the Gershgorin bound (~4 passes instead of ~15),
 // and every finer level starts at  E(own coarser levels) + [ n_l - E(neighbour's coarser levels) ]  -- the extrapolation E
 // corrected by the error it made for the neighbour.  Whether the neighbour is close enough for that (adjacent surfaces of a
