@@ -33,6 +33,9 @@ constexpr int GEO_THREADS = 128;          // axisymmetric tables: 128-point tile
 #ifndef IBS_GEO_THREADS_3D
 #define IBS_GEO_THREADS_3D 128
 #endif
+#ifndef IBS_GEO_FAST_EPILOGUE
+#define IBS_GEO_FAST_EPILOGUE 0      // see geo_point_epilogue: K1 -2 %, but the solver then ran 8-10 % SLOWER on the (2-3 ulp different) arrays -- left off
+#endif
 #ifndef IBS_GEO_KC_INLOOP
 #define IBS_GEO_KC_INLOOP 0
 #endif
@@ -163,8 +166,26 @@ __device__ __forceinline__ void geo_point_epilogue(const GeoParams& p, const Geo
     const double L_ref = p.L_ref, B_ref = 2.0 * fabs(psi_e) / (L_ref * L_ref);
     const double sgn = (psi_e > 0.0) ? 1.0 : ((psi_e < 0.0) ? -1.0 : 0.0);
     const double sqrt_s = sqrt(s_val);
-    const double B3 = B * B * B;
     const double mu0 = 4.0 * 3.141592653589793 * 1.0e-7;
+#if IBS_GEO_FAST_EPILOGUE
+    // Same formulas with ONE point-dependent reciprocal (1 / B) instead of four divisions by B, B^3, B^3 sqrt(s), psi B^2; the other
+    // divisors are per-surface constants (their reciprocals leave the fold loop).  2-3 ulp instead of 1 on these entries -- the
+    // epilogue runs 4-5 times per Newton solve on folded axisymmetric grids, where it was a third of the kernel.
+    // MEASURED (D3D bench): K1 0.588 -> 0.577 ms, but scan2_solve_kernel on the resulting arrays 2.67 -> 2.93 ms with the SAME
+    // executed instructions (1.6013e9 vs 1.6020e9), the same stalls per issue and the same warps active (ncu): not understood;
+    // the IEEE-division form stays the default.
+    const double iB = 1.0 / B, iB2 = iB * iB, iB3 = iB2 * iB;
+    const double iBref = 1.0 / B_ref, isqs = 1.0 / sqrt_s;
+    const double bmag = B * iBref;
+    const double gradpar = L_ref * (iota * Bsup_p) * iB;
+    const double gds2 = ga_ga * L_ref * L_ref * s_val;
+    const double gds21 = ga_gq * shat * iBref;
+    const double gds22 = gq_gq * (shat * shat / (L_ref * L_ref * B_ref * B_ref * s_val));
+    const double gbdrift = (-2.0 * B_ref * L_ref * L_ref * sqrt_s * sgn) * BxgB_ga * iB3;
+    const double gbdrift0 = (-2.0 * shat * isqs * sgn) * BxgB_gq * iB3;
+    const double cvdrift = gbdrift - (2.0 * B_ref * L_ref * L_ref * sqrt_s * mu0 * dpds * sgn / psi_e) * iB2;
+#else
+    const double B3 = B * B * B;
     const double bmag = B / B_ref;
     const double gradpar = L_ref * (iota * Bsup_p) / B;
     const double gds2 = ga_ga * L_ref * L_ref * s_val;
@@ -173,6 +194,7 @@ __device__ __forceinline__ void geo_point_epilogue(const GeoParams& p, const Geo
     const double gbdrift = -1.0 * 2.0 * B_ref * L_ref * L_ref * sqrt_s * BxgB_ga / B3 * sgn;
     const double gbdrift0 = -1.0 * BxgB_gq * 2.0 * shat / (B3 * sqrt_s) * sgn;
     const double cvdrift = gbdrift - 2.0 * B_ref * L_ref * L_ref * sqrt_s * mu0 * dpds * sgn / (psi_e * B * B);
+#endif
 
     const size_t line = (size_t)js * p.nalpha + ja;
     double* o = p.base_out + line * IBS_NBASE * p.nl + jl;
@@ -189,7 +211,11 @@ __device__ __forceinline__ void geo_point_epilogue(const GeoParams& p, const Geo
 }
 
 template <int NT1, int NT2>
+#if IBS_GEO_MINB > 1
 __global__ void __launch_bounds__(GeoThreads<NT1>::value, (NT1 > 0) ? IBS_GEO_MINB : 1)
+#else
+__global__ void __launch_bounds__(GeoThreads<NT1>::value)          // (a min-blocks argument of 1 lets ptxas take 254 registers: 3 instead of 4 CTAs / SM on the axisymmetric path)
+#endif
 geometry_kernel(const GeoParams p) {
     constexpr int W1 = 2 * NT1 + 1, W2 = 2 * NT2 + 1, NT = (NT1 > NT2 ? NT1 : NT2);
     constexpr int GEO_THREADS = GeoThreads<NT1>::value;
