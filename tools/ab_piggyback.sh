@@ -1,15 +1,21 @@
 #!/bin/bash
-# GPU box: does the solver execute more instructions, or the same instructions more slowly, under the two K1 epilogues?
+# GPU box: full stall breakdown of the solver kernel on the original and on the bit-truncated base arrays
 cd "$(dirname "$0")/.."
-V=$PWD/ideal-ballooning-solver_b200/lib/variants
-M=gpu__time_duration.sum,smsp__inst_executed.sum,smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio,smsp__average_warps_issue_stalled_membar_per_issue_active.ratio,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,sm__warps_active.avg.per_cycle_active
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-single > gpurun_out/r2s_plain.json 2> gpurun_out/r2s_plain.err || exit 1
-IBS_BENCH_RAMP_S=0 ncu --metrics $M --clock-control none -k regex:scan2_solve -s 3 -c 2 --csv --log-file gpurun_out/r2s_default.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-single > /dev/null 2>&1
-IBS_LIB=$V/libibs_slowepi.so IBS_BENCH_RAMP_S=0 ncu --metrics $M --clock-control none -k regex:scan2_solve -s 3 -c 2 --csv --log-file gpurun_out/r2s_slowepi.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-single > /dev/null 2>&1
+python tools/ds_one.py > /dev/null 2>&1 || exit 1
+ncu --section WarpStateStats --section SchedulerStats --section ComputeWorkloadAnalysis --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:scan2_solve -s 2 -c 1 --csv --page raw --log-file gpurun_out/ds_orig.csv python tools/ds_one.py > /dev/null 2>&1
+DS_TRUNC=1 ncu --section WarpStateStats --section SchedulerStats --section ComputeWorkloadAnalysis --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:scan2_solve -s 2 -c 1 --csv --page raw --log-file gpurun_out/ds_trunc.csv python tools/ds_one.py > /dev/null 2>&1
 python - <<'PY'
 import csv
-for n in ("default", "slowepi"):
-    rows = [r for r in csv.reader(open(f"gpurun_out/r2s_{n}.csv")) if len(r) > 10 and r[0].isdigit()]
-    for r in rows:
-        print(n, r[0], r[-3], r[-1])
+def load(n):
+    rows = list(csv.reader(open(f"gpurun_out/{n}.csv")))
+    hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    return dict(zip(rows[hdr], rows[hdr + 2]))
+a, b = load("ds_orig"), load("ds_trunc")
+for k in a:
+    try:
+        x, y = float(a[k].replace(",", "")), float(b[k].replace(",", ""))
+    except Exception:
+        continue
+    if x != 0 and abs(y - x) / abs(x) > 0.03 or "duration" in k or "inst_executed.sum" in k:
+        print(f"{k:90s} {x:14.4f} {y:14.4f}  {100 * (y - x) / x if x else 0:+.1f}%")
 PY
