@@ -506,6 +506,7 @@ int ibs_scan_host(const double* tab_mn, const double* tab_nyq, const double* sca
                 pb.base = base_c; pb.dPdrho = dp_c; pb.theta0 = (double*)(d + o_bt) + q0;
                 pb.line_of_solve = (int*)(d + o_bl) + q0; pb.nth0 = 1; pb.nsolve = (int)nq; pb.N = nl; pb.h = h;
                 pb.lam_out = (double*)(d + o_bg) + q0; pb.X_out = (double*)(d + o_xb) + q0 * nl;
+                pb.lam0 = (double*)(d + o_val) + q0;          // warm start: the maximum itself (a NaN / guarded entry fails the bracket test: cold start)
                 rc = solve_dispatch(pb, true, false, st);
                 if (rc != IBS_OK) goto done;
             } else if (xbest_out) {
